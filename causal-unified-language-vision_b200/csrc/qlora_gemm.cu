@@ -1,0 +1,359 @@
+// Host side of the tcgen05 GEMM family: tensor-map encoding, tile/launch geometry and the
+// extern "C" entry points of include/b2q.h that run on it.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "qlora_gemm.cuh"
+
+namespace b2q {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+// ---------------------------------------------------------------- tensor maps ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2D row-major tensor [outer][inner] with `pitch_bytes` between rows; box [box_outer][box_inner].
+static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner,
+                       uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return B2Q_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0) return B2Q_ERR_ARG;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    (void)elem_bytes;
+    CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : B2Q_ERR_DRIVER;
+}
+
+// bf16 operand, K-major use: tensor [rows][kdim], box 64 k x box_rows.
+static int map_bf16_kmajor(CUtensorMap* m, const void* base, int rows, int kdim, int box_rows) {
+    return make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, kdim, rows, static_cast<uint64_t>(kdim) * 2, 64,
+                       box_rows, true);
+}
+// bf16 operand, MN-major use: tensor [kdim rows][mn], box 64 mn x 64 k.
+static int map_bf16_mnmajor(CUtensorMap* m, const void* base, int kdim, int mn) {
+    return make_map_2d(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, mn, kdim, static_cast<uint64_t>(mn) * 2, 64, 64,
+                       true);
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <class Cfg>
+static int launch(GemmParams& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(qlora_gemm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        attr_set = true;
+    }
+    p.m_tiles = (p.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+    p.n_tiles = (p.N + Cfg::BN - 1) / Cfg::BN;
+    if (p.group_m <= 0) p.group_m = p.m_tiles;
+    const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
+    if (tiles == 0) return 0;
+    int pairs = num_sms() / Cfg::CG;
+    if (tiles < pairs) pairs = static_cast<int>(tiles);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pairs * Cfg::CG);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = Cfg::CG;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, qlora_gemm_kernel<Cfg>, p);
+    count_launch();
+    return static_cast<int>(e);
+}
+
+// Tuning hook: which tile configuration the two main kernels use (tests sweep it).
+static int g_variant_fwd = -1, g_variant_dx = -1;
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+static void fill_weight(GemmParams& p, const b2q_nf4_weight* w, int K_w) {
+    p.am.absmax_f32 = w->absmax;
+    p.am.absmax_q = w->absmax_q;
+    p.am.absmax2 = w->absmax2;
+    p.am.code256 = w->code256;
+    p.am.offset = w->offset;
+    p.code16 = w->code16;
+    p.kpr = K_w / 64;
+}
+
+static bool weight_ok(const b2q_nf4_weight* w) {
+    if (w == nullptr || w->packed == nullptr || w->code16 == nullptr) return false;
+    if (w->absmax_q != nullptr) return w->absmax2 != nullptr && w->code256 != nullptr;
+    return w->absmax != nullptr;
+}
+
+//                  CG MT  BN  A_MN   B_MN   B_DEC EPI       STAGES
+using FwdV0 = GemmCfg<1, 1, 128, false, false, true, EPI_BF16, 4>;
+using FwdV1 = GemmCfg<1, 2, 128, false, false, true, EPI_BF16, 4>;
+using FwdV2 = GemmCfg<2, 1, 256, false, false, true, EPI_BF16, 4>;
+using FwdV3 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4>;
+using DxV0 = GemmCfg<1, 1, 128, false, true, true, EPI_BF16, 4>;
+using DxV1 = GemmCfg<1, 2, 128, false, true, true, EPI_BF16, 4>;
+using DxV2 = GemmCfg<2, 1, 256, false, true, true, EPI_BF16, 4>;
+using DxV3 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4>;
+
+template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, 6>;   // u = xd A^T
+template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, 6>;      // du = s dy B
+template <int R> using GradACfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6>;  // dA^T tile, stored transposed
+template <int R> using GradBCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART, 6>;    // dB tile
+using GemmKN = GemmCfg<1, 1, 128, false, true, false, EPI_BF16, 6>;   // b given [K,N]
+using GemmNK = GemmCfg<1, 1, 128, false, false, false, EPI_BF16, 6>;  // b given [N,K]
+
+}  // namespace b2q
+
+using namespace b2q;
+
+extern "C" int b2q_version(void) { return B2Q_VERSION; }
+
+extern "C" uint64_t b2q_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" const char* b2q_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case B2Q_ERR_SHAPE: return "b2q: shape / divisibility contract violated";
+        case B2Q_ERR_ARG: return "b2q: invalid pointer arguments";
+        case B2Q_ERR_DRIVER: return "b2q: CUDA driver tensor-map encode unavailable or failed";
+        case B2Q_ERR_WORKSPACE: return "b2q: workspace too small";
+        default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "b2q: unknown error";
+    }
+}
+
+extern "C" int b2q_set_variant(int fwd_variant, int dx_variant) {
+    g_variant_fwd = fwd_variant;
+    g_variant_dx = dx_variant;
+    return 0;
+}
+
+extern "C" int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void* us, const void* lora_B, void* y,
+                             int M, int N, int K, int r, cudaStream_t stream) {
+    if (M == 0) return 0;
+    if (!weight_ok(w) || x == nullptr || y == nullptr) return B2Q_ERR_ARG;
+    const bool lora = us != nullptr && lora_B != nullptr && r > 0;
+    if (M < 0 || K % 64 != 0 || N % 256 != 0 || (lora && r % 64 != 0)) return B2Q_ERR_SHAPE;
+    int variant = g_variant_fwd >= 0 ? g_variant_fwd : env_int("B2Q_FWD_VARIANT", 3);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    fill_weight(p, w, K);
+    p.D = y; p.D2 = nullptr; p.ldd = N; p.alpha = 1.f; p.alpha2 = 0.f;
+    p.M = M; p.N = N; p.kb_main = K / 64; p.kb_tail = lora ? r / 64 : 0; p.splits = 1;
+    int e = 0;
+    auto setup = [&](int bnc, int group_m) -> int {
+        p.group_m = group_m;
+        if ((e = map_bf16_kmajor(&p.tmA, x, M, K, 128))) return e;
+        if ((e = make_map_2d(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->packed, K / 2, N, K / 2, 32, bnc, false)))
+            return e;
+        if (lora) {
+            if ((e = map_bf16_kmajor(&p.tmA2, us, M, r, 128))) return e;
+            if ((e = map_bf16_kmajor(&p.tmB2, lora_B, N, r, bnc))) return e;
+        }
+        return 0;
+    };
+    // L2 slab: keep (group_m * TILE_M) x K of activations (bf16) around 32 MB
+    auto slab = [&](int tile_m) { int g = static_cast<int>((32ll << 20) / (2ll * K * tile_m)); return g < 1 ? 1 : g; };
+    switch (variant) {
+        case 0: if ((e = setup(FwdV0::BNC, slab(FwdV0::TILE_M)))) return e; return launch<FwdV0>(p, stream);
+        case 1: if ((e = setup(FwdV1::BNC, slab(FwdV1::TILE_M)))) return e; return launch<FwdV1>(p, stream);
+        case 2: if ((e = setup(FwdV2::BNC, slab(FwdV2::TILE_M)))) return e; return launch<FwdV2>(p, stream);
+        default: if ((e = setup(FwdV3::BNC, slab(FwdV3::TILE_M)))) return e; return launch<FwdV3>(p, stream);
+    }
+}
+
+extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A, void* dx,
+                                int M, int N, int K, int r, cudaStream_t stream) {
+    if (M == 0) return 0;
+    if (!weight_ok(w) || dy == nullptr || dx == nullptr) return B2Q_ERR_ARG;
+    const bool lora = du != nullptr && lora_A != nullptr && r > 0;
+    if (M < 0 || N % 64 != 0 || K % 256 != 0 || (lora && r % 64 != 0)) return B2Q_ERR_SHAPE;
+    int variant = g_variant_dx >= 0 ? g_variant_dx : env_int("B2Q_DX_VARIANT", 3);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    fill_weight(p, w, K);
+    p.D = dx; p.D2 = nullptr; p.ldd = K; p.alpha = 1.f; p.alpha2 = 0.f;
+    p.M = M; p.N = K; p.kb_main = N / 64; p.kb_tail = lora ? r / 64 : 0; p.splits = 1;
+    int e = 0;
+    auto setup = [&](int bnc, int group_m) -> int {
+        p.group_m = group_m;
+        if ((e = map_bf16_kmajor(&p.tmA, dy, M, N, 128))) return e;
+        // packed W [N rows][K/2 bytes]: box (bnc/2 bytes) x 64 rows
+        if ((e = make_map_2d(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->packed, K / 2, N, K / 2, bnc / 2, 64, false)))
+            return e;
+        if (lora) {
+            if ((e = map_bf16_kmajor(&p.tmA2, du, M, r, 128))) return e;
+            if ((e = map_bf16_mnmajor(&p.tmB2, lora_A, r, K))) return e;
+        }
+        return 0;
+    };
+    auto slab = [&](int tile_m) { int g = static_cast<int>((32ll << 20) / (2ll * N * tile_m)); return g < 1 ? 1 : g; };
+    switch (variant) {
+        case 0: if ((e = setup(DxV0::BNC, slab(DxV0::TILE_M)))) return e; return launch<DxV0>(p, stream);
+        case 1: if ((e = setup(DxV1::BNC, slab(DxV1::TILE_M)))) return e; return launch<DxV1>(p, stream);
+        case 2: if ((e = setup(DxV2::BNC, slab(DxV2::TILE_M)))) return e; return launch<DxV2>(p, stream);
+        default: if ((e = setup(DxV3::BNC, slab(DxV3::TILE_M)))) return e; return launch<DxV3>(p, stream);
+    }
+}
+
+template <int R>
+static int lora_down_r(const void* xd, const void* lora_A, float scale, void* u, void* us, int M, int K,
+                       cudaStream_t stream) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.D = u; p.D2 = us; p.ldd = R; p.alpha = 1.f; p.alpha2 = scale;
+    p.M = M; p.N = R; p.kb_main = K / 64; p.kb_tail = 0; p.splits = 1;
+    int e;
+    if ((e = map_bf16_kmajor(&p.tmA, xd, M, K, 128))) return e;
+    if ((e = map_bf16_kmajor(&p.tmB, lora_A, R, K, R))) return e;
+    return launch<DownCfg<R>>(p, stream);
+}
+
+extern "C" int b2q_lora_down(const void* xd, const void* lora_A, float scale, void* u, void* us, int M, int K, int r,
+                             cudaStream_t stream) {
+    if (M == 0) return 0;
+    if (xd == nullptr || lora_A == nullptr || u == nullptr) return B2Q_ERR_ARG;
+    if (K % 64 != 0) return B2Q_ERR_SHAPE;
+    if (r == 64) return lora_down_r<64>(xd, lora_A, scale, u, us, M, K, stream);
+    if (r == 128) return lora_down_r<128>(xd, lora_A, scale, u, us, M, K, stream);
+    return B2Q_ERR_SHAPE;
+}
+
+template <int R>
+static int lora_du_r(const void* dy, const void* lora_B, float scale, void* du, int M, int N, cudaStream_t stream) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.D = du; p.D2 = nullptr; p.ldd = R; p.alpha = scale;
+    p.M = M; p.N = R; p.kb_main = N / 64; p.kb_tail = 0; p.splits = 1;
+    int e;
+    if ((e = map_bf16_kmajor(&p.tmA, dy, M, N, 128))) return e;
+    if ((e = map_bf16_mnmajor(&p.tmB, lora_B, N, R))) return e;  // lora_B [N][r]: contraction rows, r contiguous
+    return launch<DuCfg<R>>(p, stream);
+}
+
+extern "C" int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, void* du, int M, int N, int r,
+                               cudaStream_t stream) {
+    if (M == 0) return 0;
+    if (dy == nullptr || lora_B == nullptr || du == nullptr) return B2Q_ERR_ARG;
+    if (N % 64 != 0) return B2Q_ERR_SHAPE;
+    if (r == 64) return lora_du_r<64>(dy, lora_B, scale, du, M, N, stream);
+    if (r == 128) return lora_du_r<128>(dy, lora_B, scale, du, M, N, stream);
+    return B2Q_ERR_SHAPE;
+}
+
+static int grad_splits(int out_tiles, int kblocks) {
+    int s = num_sms() / (out_tiles > 0 ? out_tiles : 1);
+    if (s < 1) s = 1;
+    if (s > kblocks) s = kblocks > 0 ? kblocks : 1;
+    if (s > 32) s = 32;
+    return s;
+}
+
+extern "C" size_t b2q_lora_grads_workspace_bytes(int M, int N, int K, int r) {
+    const int kblocks = (M + 63) / 64;
+    const size_t a = static_cast<size_t>(grad_splits(K / 128, kblocks)) * r * K * sizeof(float);
+    const size_t b = static_cast<size_t>(grad_splits(N / 128, kblocks)) * N * r * sizeof(float);
+    return a + b + 256;
+}
+
+template <int R>
+static int lora_grads_r(const void* dy, const void* xd, const void* u, const void* du, float scale, void* dA, void* dB,
+                        int accumulate, float* ws, int M, int N, int K, cudaStream_t stream) {
+    const int kblocks = (M + 63) / 64;
+    int e;
+    // dA^T[k, j] = sum_m xd[m, k] * du[m, j]   (A = xd^T MN-major, B = du MN-major), stored transposed -> [r][K]
+    const int sa = grad_splits(K / 128, kblocks);
+    float* wa = ws;
+    {
+        GemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.D = wa; p.M = K; p.N = R; p.splits = sa; p.kb_main = (kblocks + sa - 1) / sa; p.kb_tail = 0;
+        if ((e = map_bf16_mnmajor(&p.tmA, xd, M, K))) return e;
+        if ((e = map_bf16_mnmajor(&p.tmB, du, M, R))) return e;
+        if ((e = launch<GradACfg<R>>(p, stream))) return e;
+        if ((e = b2q_reduce_partials(wa, sa, static_cast<int64_t>(R) * K, 1.0f, dA, accumulate, stream))) return e;
+    }
+    // dB[n, j] = scale * sum_m dy[m, n] * u[m, j]
+    const int sb = grad_splits(N / 128, kblocks);
+    float* wb = ws + static_cast<size_t>(sa) * R * K;
+    {
+        GemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.D = wb; p.M = N; p.N = R; p.splits = sb; p.kb_main = (kblocks + sb - 1) / sb; p.kb_tail = 0;
+        if ((e = map_bf16_mnmajor(&p.tmA, dy, M, N))) return e;
+        if ((e = map_bf16_mnmajor(&p.tmB, u, M, R))) return e;
+        if ((e = launch<GradBCfg<R>>(p, stream))) return e;
+        if ((e = b2q_reduce_partials(wb, sb, static_cast<int64_t>(N) * R, scale, dB, accumulate, stream))) return e;
+    }
+    return 0;
+}
+
+extern "C" int b2q_lora_grads(const void* dy, const void* xd, const void* u, const void* du, float scale, void* dA,
+                              void* dB, int accumulate, void* workspace, size_t workspace_bytes, int M, int N, int K,
+                              int r, cudaStream_t stream) {
+    if (dy == nullptr || xd == nullptr || u == nullptr || du == nullptr || dA == nullptr || dB == nullptr ||
+        workspace == nullptr)
+        return B2Q_ERR_ARG;
+    if (K % 128 != 0 || N % 128 != 0 || M <= 0) return B2Q_ERR_SHAPE;
+    if (workspace_bytes < b2q_lora_grads_workspace_bytes(M, N, K, r)) return B2Q_ERR_WORKSPACE;
+    float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
+    if (r == 64) return lora_grads_r<64>(dy, xd, u, du, scale, dA, dB, accumulate, ws, M, N, K, stream);
+    if (r == 128) return lora_grads_r<128>(dy, xd, u, du, scale, dA, dB, accumulate, ws, M, N, K, stream);
+    return B2Q_ERR_SHAPE;
+}
+
+extern "C" int b2q_gemm_bf16(const void* a, const void* b, int b_is_kn, float alpha, void* d, int M, int N, int K,
+                             cudaStream_t stream) {
+    if (M == 0) return 0;
+    if (a == nullptr || b == nullptr || d == nullptr) return B2Q_ERR_ARG;
+    if (K % 64 != 0 || N % 128 != 0) return B2Q_ERR_SHAPE;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.D = d; p.ldd = N; p.alpha = alpha; p.M = M; p.N = N; p.kb_main = K / 64; p.splits = 1;
+    int e;
+    if ((e = map_bf16_kmajor(&p.tmA, a, M, K, 128))) return e;
+    if (b_is_kn) {
+        if ((e = map_bf16_mnmajor(&p.tmB, b, K, N))) return e;
+        return launch<GemmKN>(p, stream);
+    }
+    if ((e = map_bf16_kmajor(&p.tmB, b, N, K, 128))) return e;
+    return launch<GemmNK>(p, stream);
+}

@@ -1,0 +1,419 @@
+// Warp-specialised, persistent tcgen05 GEMM for sm_100a with an optional in-main-loop NF4
+// decode of the B operand.  One template, instantiated for every GEMM on the QLoRA path:
+//
+//   D[M,N] = sum over main k-blocks  A[M, 64] * Bop[64, N]      (Bop: bf16 via TMA, or NF4 decoded)
+//          + sum over tail k-blocks  A2[M, 64] * B2[64, N]      (LoRA tail, bf16 via TMA)
+//
+// Roles (one CTA per SM, or a CTA pair with cta_group::2):
+//   warp 0      TMA producer          warp 1      UMMA issuer (leader CTA only)
+//   warp 2      TMEM allocator        warps 4-7   epilogue (TMEM -> registers -> global)
+//   warps 8..   NF4 decode (B_DEC): packed bytes (TMA-staged smem) -> registers (LUT/PRMT)
+//               -> bf16 in the canonical 128B-swizzled UMMA operand layout in smem
+//
+// Shared memory per stage: A tile (MT x 128 rows x 64 k bf16), B tile (BNC rows x 64 k bf16),
+// packed-NF4 tile (BNC x 32 B).  A stage is released by tcgen05.commit when the MMAs that read
+// it have finished.  The bf16 weight only ever exists in shared memory.
+//
+// Operand layouts (both 128B-swizzled, see b2q_ptx.cuh umma_desc_sw128):
+//   K-major  tile [rows x 64 k]: row r at (r/8)*1024 + (r%8)*128, 16-byte chunk c at (c ^ (r%8))*16
+//   MN-major tile [64 k x mn]  : same image with "row" = contraction index and 64-element chunks
+//                                of the MN dimension 8192 B apart (LBO), 8-row groups 1024 B (SBO)
+// so one decode routine (one thread = one 64-weight quantisation block = one 128-byte row) serves
+// the forward GEMM (W is K-major) and the dX GEMM (W is MN-major) alike.
+#pragma once
+#include "b2q_decode.cuh"
+#include "b2q_internal.h"
+#include "b2q_ptx.cuh"
+
+namespace b2q {
+
+enum EpiKind : int {
+    EPI_BF16 = 0,      // D bf16 [M, ldd] = alpha * acc   (+ optional D2 = alpha2 * acc)
+    EPI_F32_PART = 1,  // fp32 partial [split][M][N]
+    EPI_F32_PART_T = 2 // fp32 partial, transposed [split][N][M]
+};
+
+struct GemmParams {
+    CUtensorMap tmA;   // main A operand (bf16)
+    CUtensorMap tmA2;  // tail A operand (bf16)
+    CUtensorMap tmB;   // main B operand: bf16, or packed NF4 bytes when B_DEC
+    CUtensorMap tmB2;  // tail B operand (bf16)
+    AbsmaxSrc am;
+    const float* code16;
+    void* D;
+    void* D2;
+    long long ldd;     // row pitch of D / D2 in elements (EPI_BF16)
+    float alpha, alpha2;
+    int M, N;          // extents of D
+    int kb_main;       // main k-blocks per tile (per split)
+    int kb_tail;       // tail k-blocks per tile
+    int splits;        // split-K factor (EPI_F32_PART*), else 1
+    int kpr;           // absmax blocks per W row (= K_w / 64)          (B_DEC)
+    int m_tiles, n_tiles;
+    int group_m;       // rasterisation: m-tiles per L2 slab
+};
+
+template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_>
+struct GemmCfg {
+    static constexpr int CG = CG_;          // CTAs per MMA (cta_group)
+    static constexpr int MT = MT_;          // 128-row accumulators per CTA
+    static constexpr int BN = BN_;          // UMMA N (whole pair)
+    static constexpr bool A_MN = A_MN_;
+    static constexpr bool B_MN = B_MN_;
+    static constexpr bool B_DEC = B_DEC_;
+    static constexpr int EPI = EPI_;
+    static constexpr int STAGES = STAGES_;
+
+    static constexpr int BNC = BN / CG;                 // B rows held (and decoded) by one CTA
+    static constexpr int TILE_M = 128 * MT * CG;        // rows of D per tile (pair)
+    static constexpr int A_BYTES = MT * 128 * 64 * 2;
+    static constexpr int B_BYTES = BNC * 64 * 2;
+    static constexpr int P_BYTES = B_DEC ? BNC * 32 : 0;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + P_BYTES;
+    static constexpr int ACC_COLS = MT * BN;
+    static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS_RAW = ACC_COLS * ACC_STAGES;
+    static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
+                                     : TMEM_COLS_RAW <= 256 ? 256 : 512;
+    static constexpr int NDT = B_DEC ? BNC : 0;         // decode threads
+    static constexpr int NDW = NDT / 32;
+    static constexpr int THREADS = 256 + NDT;
+    static constexpr int BAR_BYTES = 1024;              // barriers + tmem ptr + code256
+    static constexpr int CODE256_BYTES = B_DEC ? 1024 : 0;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES + CODE256_BYTES;
+
+    static_assert(BN % (16 * CG) == 0 && BN <= 256, "UMMA N");
+    static_assert(ACC_COLS <= 512, "TMEM columns");
+    static_assert(!B_DEC || (BNC % 64 == 0), "decode tile");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
+
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& mt, int& nt, int& split) {
+    // split fastest, then m inside an L2 slab of group_m m-tiles, then n, then slab.
+    split = tile % p.splits;
+    int t = tile / p.splits;
+    const int per_slab = p.group_m * p.n_tiles;
+    const int slab = t / per_slab;
+    const int m_first = slab * p.group_m;
+    const int m_cnt = min(p.group_m, p.m_tiles - m_first);
+    const int within = t - slab * per_slab;
+    nt = within / m_cnt;
+    mt = m_first + within % m_cnt;
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int CG = Cfg::CG, MT = Cfg::MT, BN = Cfg::BN, BNC = Cfg::BNC, STAGES = Cfg::STAGES;
+    constexpr int ACC_STAGES = Cfg::ACC_STAGES, ACC_COLS = Cfg::ACC_COLS;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto pk_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + ACC_STAGES + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 2 * ACC_STAGES);
+    volatile uint32_t* tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 2 * ACC_STAGES));
+    float* code256_s = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+
+    auto a_stage = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+    auto b_stage = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+    auto p_stage = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + Cfg::B_BYTES; };
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int pair_id = blockIdx.x / CG;
+    const int num_pairs = gridDim.x / CG;
+    const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
+    const int kb_total = p.kb_main + p.kb_tail;
+
+    // ---------------------------------------------------------------- setup ----
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        if (p.kb_tail > 0) {
+            tma_prefetch_desc(&p.tmA2);
+            tma_prefetch_desc(&p.tmB2);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), CG * (1 + Cfg::NDW));  // per CTA: producer (+tx) + one arrive per decode warp
+            mbar_init(empty_bar(s), 1);                   // tcgen05.commit
+            mbar_init(pk_bar(s), 1);                      // producer (+tx)
+        }
+        for (int a = 0; a < ACC_STAGES; ++a) {
+            mbar_init(tfull_bar(a), 1);                   // tcgen05.commit
+            mbar_init(tempty_bar(a), CG * 4);             // one arrive per epilogue warp, both CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish<CG>();
+    }
+    if constexpr (Cfg::B_DEC) {
+        if (p.am.absmax_q != nullptr)
+            for (int i = threadIdx.x; i < 256; i += Cfg::THREADS) code256_s[i] = __ldg(p.am.code256 + i);
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    // barrier addresses as seen for an arrive: the leader's copy when working as a pair
+    auto full_bar_arrive = [&](int s) { return CG == 2 ? mapa(full_bar(s), 0) : full_bar(s); };
+    auto tempty_bar_arrive = [&](int a) { return CG == 2 ? mapa(tempty_bar(a), 0) : tempty_bar(a); };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer ====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                int mt_i, nt_i, split;
+                tile_coords(p, tile, mt_i, nt_i, split);
+                const int m0 = mt_i * Cfg::TILE_M;
+                const int n0 = nt_i * BN;
+                const int kb0 = split * p.kb_main;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    const bool tail = kb >= p.kb_main;
+                    const int k0 = tail ? (kb - p.kb_main) * 64 : (kb0 + kb) * 64;
+                    const CUtensorMap* mapA = tail ? &p.tmA2 : &p.tmA;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const bool b_by_tma = tail || !Cfg::B_DEC;
+                    const uint32_t tx = Cfg::A_BYTES + (b_by_tma ? Cfg::B_BYTES : 0);
+                    const uint32_t fb = full_bar_arrive(s);
+                    if constexpr (CG == 2) mbar_arrive_expect_tx_cluster(fb, tx); else mbar_arrive_expect_tx(fb, tx);
+                    auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+                        if constexpr (CG == 2) tma_load_2d_pair(dst, map, fb, c0, c1); else tma_load_2d(dst, map, fb, c0, c1);
+                    };
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int row0 = m0 + (CG == 2 ? mt * 256 + static_cast<int>(rank) * 128 : mt * 128);
+                        const uint32_t dst = a_stage(s) + mt * 16384;
+                        if constexpr (!Cfg::A_MN) {
+                            load(dst, mapA, k0, row0);                 // box 64 k x 128 rows
+                        } else {
+                            load(dst, mapA, row0, k0);                 // box 64 mn x 64 k, two MN chunks
+                            load(dst + 8192, mapA, row0 + 64, k0);
+                        }
+                    }
+                    const int brow0 = n0 + static_cast<int>(rank) * BNC;
+                    if (b_by_tma) {
+                        const CUtensorMap* mapB = tail ? &p.tmB2 : &p.tmB;
+                        if constexpr (!Cfg::B_MN) {
+                            load(b_stage(s), mapB, k0, brow0);         // box 64 k x BNC rows
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < BNC / 64; ++c) load(b_stage(s) + c * 8192, mapB, brow0 + c * 64, k0);
+                        }
+                    } else {
+                        mbar_arrive_expect_tx(pk_bar(s), Cfg::P_BYTES);
+                        if constexpr (!Cfg::B_MN)
+                            tma_load_2d(p_stage(s), &p.tmB, pk_bar(s), k0 / 2, brow0);    // box 32 B x BNC rows of W
+                        else
+                            tma_load_2d(p_stage(s), &p.tmB, pk_bar(s), brow0 / 2, k0);    // box BNC/2 B x 64 rows of W
+                    }
+                    // tail rounds: nothing to decode, but pk_bar must advance one phase per ring
+                    // round so the decode warps' parity stays in lockstep with the ring
+                    if (Cfg::B_DEC && tail) mbar_arrive(pk_bar(s));
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+            // drain: every tcgen05.commit aimed at this CTA's empty barriers has landed before exit
+            for (int i = 0; i < STAGES; ++i) {
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ====================================================== UMMA issuer ====
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, Cfg::A_MN ? 1 : 0, Cfg::B_MN ? 1 : 0);
+            int s = 0;
+            uint32_t ph = 0;
+            int as = 0;
+            uint32_t aph = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(tempty_bar(as), aph ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t d_tmem = tmem_base + as * ACC_COLS + mt * BN;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adesc =
+                                Cfg::A_MN ? umma_desc_sw128(a_stage(s) + mt * 16384 + k * 2048, 8192, 1024)
+                                          : umma_desc_sw128(a_stage(s) + mt * 16384 + k * 32, 16, 1024);
+                            const uint64_t bdesc = Cfg::B_MN ? umma_desc_sw128(b_stage(s) + k * 2048, 8192, 1024)
+                                                             : umma_desc_sw128(b_stage(s) + k * 32, 16, 1024);
+                            umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
+                    if (kb == kb_total - 1) umma_commit<CG>(tfull_bar(as));
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+                if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ========================================================= epilogue ====
+        const int wq = warp & 3;  // TMEM lane quadrant this warp may access
+        int as = 0;
+        uint32_t aph = 0;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            int mt_i, nt_i, split;
+            tile_coords(p, tile, mt_i, nt_i, split);
+            const int m0 = mt_i * Cfg::TILE_M;
+            const int n0 = nt_i * BN;
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int row = m0 + (CG == 2 ? mt * 256 + static_cast<int>(rank) * 128 : mt * 128) + wq * 32 + lane;
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * ACC_COLS + mt * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    const int col0 = n0 + c * 32;
+                    if (row < p.M && col0 < p.N) {
+                        if constexpr (Cfg::EPI == EPI_BF16) {
+                            uint32_t o[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                o[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.alpha,
+                                                   __uint_as_float(v[2 * j + 1]) * p.alpha);
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) +
+                                                                  static_cast<long long>(row) * p.ldd + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                            if (p.D2 != nullptr) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    o[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.alpha2,
+                                                       __uint_as_float(v[2 * j + 1]) * p.alpha2);
+                                uint4* dst2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D2) +
+                                                                       static_cast<long long>(row) * p.ldd + col0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    dst2[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                            }
+                        } else if constexpr (Cfg::EPI == EPI_F32_PART) {
+                            float* dst = reinterpret_cast<float*>(p.D) +
+                                         (static_cast<long long>(split) * p.M + row) * p.N + col0;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                reinterpret_cast<uint4*>(dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            float* dst = reinterpret_cast<float*>(p.D) +
+                                         (static_cast<long long>(split) * p.N + col0) * p.M + row;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.M] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar_arrive(as)); else mbar_arrive(tempty_bar(as));
+            }
+            if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+        }
+    } else if (Cfg::B_DEC && warp >= 8) {
+        // ======================================================= NF4 decode ====
+        const int t = threadIdx.x - 256;  // one thread = one quantisation block per stage
+        float code16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) code16[i] = __ldg(p.code16 + i);
+        const bool nested = p.am.absmax_q != nullptr;
+        auto absmax_of = [&](long long blk) -> float {
+            if (!nested) return __ldg(p.am.absmax_f32 + blk);
+            const float c = code256_s[__ldg(p.am.absmax_q + blk)];
+            return __fadd_rn(__fmul_rn(c, __ldg(p.am.absmax2 + (blk >> 8))), p.am.offset);
+        };
+        // destination row of this thread inside the B stage and its swizzle key
+        constexpr int PARTS = BNC / 64;  // MN-major: 64-wide chunks of the output dimension
+        const int r_loc = Cfg::B_MN ? t / PARTS : t;
+        const int part = Cfg::B_MN ? t % PARTS : 0;
+        const uint32_t dst_off = Cfg::B_MN ? static_cast<uint32_t>((part * 8 + (r_loc >> 3)) * 1024 + (r_loc & 7) * 128)
+                                           : static_cast<uint32_t>((r_loc >> 3) * 1024 + (r_loc & 7) * 128);
+        const uint32_t key = static_cast<uint32_t>(r_loc & 7);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            int mt_i, nt_i, split;
+            tile_coords(p, tile, mt_i, nt_i, split);
+            const int n0 = nt_i * BN + static_cast<int>(rank) * BNC;
+            // absmax block index of k-block kb:  K-major: (n0 + t) * kpr + kb
+            //                                    MN-major: (kb*64 + r_loc) * kpr + (n0 + part*64)/64
+            long long blk = Cfg::B_MN ? static_cast<long long>(r_loc) * p.kpr + (n0 >> 6) + part
+                                      : static_cast<long long>(n0 + t) * p.kpr;
+            const long long blk_step = Cfg::B_MN ? 64LL * p.kpr : 1LL;
+            blk += static_cast<long long>(split) * p.kb_main * blk_step;
+            float a_next = p.kb_main > 0 ? absmax_of(blk) : 0.f;
+            for (int kb = 0; kb < p.kb_main; ++kb) {
+                const float a = a_next;
+                blk += blk_step;
+                if (kb + 1 < p.kb_main) a_next = absmax_of(blk);  // prefetch one k-block ahead
+                Nf4Lut lut;
+                nf4_build_lut(code16, a, lut);
+                mbar_wait(pk_bar(s), ph);
+                uint32_t w[8];
+                {
+                    const uint32_t src = p_stage(s) + t * 32;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src));
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(src + 16));
+                }
+                const uint32_t dst = b_stage(s) + dst_off;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t o[4];
+                    nf4_decode_word(w[j], lut, o);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + ((static_cast<uint32_t>(j) ^ key) << 4)),
+                                 "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(full_bar_arrive(s)); else mbar_arrive(full_bar(s));
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+            for (int kb = 0; kb < p.kb_tail; ++kb) {  // LoRA tail: B arrives by TMA, just keep the count
+                mbar_wait(pk_bar(s), ph);
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(full_bar_arrive(s)); else mbar_arrive(full_bar(s));
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------- teardown ----
+    __syncwarp();  // single-lane roles (producer, UMMA issuer) rejoin their warp before the aligned barrier
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace b2q

@@ -1,0 +1,154 @@
+/* b2q.h -- C ABI of the B200-native QLoRA linear hot path (libb2q.so).
+ *
+ * Drop-in boundary for the one path the reference (LTTTDH/Causal-Unified-Language-Vision)
+ * spends its training time in: the NF4 `Linear4bit` base weight + PEFT LoRA adapter of the
+ * causal-LM decoder projections, forward and backward.  The reference reaches that path
+ * only through third-party libraries (bitsandbytes' ctypes C ABI + cuBLAS via torch); this
+ * header is what a replacement `.so` exports in their place.  Every entry point cites the
+ * reference-side interface it stands in for.  Conventions (same as bitsandbytes' C ABI):
+ *
+ *   - plain device pointers and sizes, no torch / C++ types; all buffers caller-owned,
+ *     contiguous, row-major, 16-byte aligned; nothing persistent is allocated inside
+ *   - every call is asynchronous on the given `cudaStream_t` and does no synchronisation
+ *   - return value: 0 on success, a cudaError_t (> 0) or a B2Q_ERR_* code (< 0) on failure;
+ *     the library never calls exit() (bitsandbytes' CUDA_CHECK_RETURN does -- not copied)
+ *   - there is NO CPU implementation behind any of these; without a sm_100a device the
+ *     launches fail with a CUDA error and the Python host layer raises
+ *
+ * NF4 layout (bitsandbytes `Params4bit` / `QuantState`):
+ *   packed   uint8[(N*K)/2]   element i of row-major W[N,K] in byte i/2, EVEN i in the HIGH nibble
+ *   absmax   fp32[N*K/64]                     (plain), or
+ *   absmax_q uint8[N*K/64] + absmax2 fp32[ceil(N*K/64/256)] + code256 fp32[256] + offset (double quant)
+ *   code16   fp32[16]  the NF4 code book ("quant_map"), an INPUT, not a compile-time constant
+ */
+#ifndef B2Q_H_
+#define B2Q_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define B2Q_VERSION 100
+
+#define B2Q_ERR_SHAPE (-1)   /* shape / divisibility contract violated            */
+#define B2Q_ERR_ARG (-2)     /* null / inconsistent pointer arguments             */
+#define B2Q_ERR_DRIVER (-3)  /* CUDA driver entry point (tensor-map encode) failed */
+#define B2Q_ERR_WORKSPACE (-4) /* workspace too small                             */
+
+/* One NF4-quantised weight W[N,K] (blocksize 64).  Exactly one of absmax / absmax_q is set. */
+typedef struct b2q_nf4_weight {
+    const uint8_t* packed;
+    const float* absmax;     /* plain absmax, or NULL when double-quantised */
+    const uint8_t* absmax_q; /* double quant: 8-bit codes of (absmax - offset), or NULL */
+    const float* absmax2;    /* double quant: one fp32 scale per 256 absmax blocks      */
+    const float* code256;    /* double quant: 256-entry dynamic map                     */
+    float offset;            /* double quant: mean of the absmax vector                 */
+    const float* code16;     /* 16-entry NF4 code book                                  */
+} b2q_nf4_weight;
+
+int b2q_version(void);
+const char* b2q_error_string(int code);
+
+/* ---- NF4 blockwise quantise / dequantise ------------------------------------------------ */
+
+/* W_bf16[i] = bf16_rn(code16[nibble(i)] * absmax_f32[i/64]),  nested absmax decoded as
+ * fl32(fl32(code256[q] * absmax2[j/256]) + offset).  Bit-exact with the reference decode.
+ * algo 0: straightforward per-element path; algo 1: the pre-scaled-LUT/PRMT path the GEMM
+ * main loops use (exported so its bit-exactness can be checked in isolation).
+ * Replaces bitsandbytes `cdequantize_blockwise_bf16_nf4` (+ nested `cdequantize_blockwise_fp32`
+ * and the `absmax += offset` torch op), called from `bnb.functional.dequantize_4bit`, which the
+ * reference triggers on every wrapped linear via cullavo/arch_cullavo.py:638. */
+int b2q_nf4_decode(const uint8_t* packed, const float* absmax, const uint8_t* absmax_q, const float* absmax2,
+                   const float* code256, float offset, const float* code16, void* out_bf16, int64_t n,
+                   int blocksize, int algo, cudaStream_t stream);
+
+/* Blockwise(64) NF4 quantisation of n fp32 / bf16 values: absmax[j] = max|w|, code = number of
+ * NF4 mid-point thresholds strictly below w * (1.0f / absmax), two codes per byte (even element
+ * high).  Replaces `cquantize_blockwise_{fp32,bf16}_nf4`, run by `Params4bit.cuda()` during
+ * `from_pretrained` at cullavo/load_cullavo.py:86. */
+int b2q_nf4_quantize(const void* w, int w_is_bf16, int64_t n, uint8_t* packed, float* absmax, cudaStream_t stream);
+
+/* Double quantisation of the absmax vector: offset = mean(absmax); (absmax - offset) quantised
+ * blockwise(256) to the nearest code256 entry.  Replaces the nested `quantize_blockwise` call in
+ * `bnb.functional.quantize_4bit(compress_statistics=True)` (cullavo/load_cullavo.py:80). */
+int b2q_absmax_double_quant(const float* absmax, int64_t nblocks, const float* code256, uint8_t* absmax_q,
+                            float* absmax2, float* offset_out, cudaStream_t stream);
+
+/* ---- LoRA-branch dropout (PEFT `lora_dropout`, cullavo/load_cullavo.py:98,107) ---------- */
+
+/* mask[i] = keep(seed, i) in {0,1};  keep is a counter-based hash so forward, backward and the
+ * CPU oracle regenerate the same mask from (seed, p).  Torch's Philox stream is not reproduced
+ * (SURVEY.md section 7.3). */
+int b2q_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, float p, cudaStream_t stream);
+/* xd = bf16(x * keep / (1 - p)) */
+int b2q_dropout_apply(const void* x_bf16, void* xd_bf16, int64_t n, uint64_t seed, float p, cudaStream_t stream);
+/* dx[i] += bf16(dxl[i] * keep / (1 - p))  (backward of the dropout on the LoRA branch) */
+int b2q_dropout_bwd_add(void* dx_bf16, const void* dxl_bf16, int64_t n, uint64_t seed, float p,
+                        cudaStream_t stream);
+
+/* ---- QLoRA linear: tcgen05 / TMEM / TMA kernels ----------------------------------------- *
+ * Shapes: x [M,K], W [N,K] (NF4), lora_A [r,K], lora_B [N,r], y / dy [M,N], u / du [M,r], all bf16
+ * unless noted.  Contract: K % 64 == 0, N % 64 == 0, r in {16,32,64,128,256} and r % 16 == 0
+ * for the LoRA operands (r % 64 == 0 for the fused tails), 16-byte aligned rows.           */
+
+/* u = xd @ lora_A^T  (fp32 accumulate -> bf16);  us = bf16(scale * u) when us != NULL.
+ * Replaces `lora_A(dropout(x))` in peft.tuners.lora.bnb.Linear4bit.forward. */
+int b2q_lora_down(const void* xd, const void* lora_A, float scale, void* u, void* us, int M, int K, int r,
+                  cudaStream_t stream);
+
+/* y = x @ dequant(W)^T + us @ lora_B^T  in one kernel: packed NF4 staged by TMA, decoded in
+ * registers, written to swizzled shared memory, consumed by tcgen05.mma with the accumulator in
+ * TMEM; the LoRA up-projection runs as extra K-blocks into the same accumulator.  The bf16
+ * weight never exists in HBM.  us may be NULL (adapter disabled / base only).
+ * Replaces `bnb.matmul_4bit` -> `MatMul4Bit.forward` (dequantize_4bit + cuBLAS `F.linear`) plus
+ * `result + lora_B(...) * scaling` of the PEFT wrapper. */
+int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void* us, const void* lora_B, void* y, int M, int N,
+                  int K, int r, cudaStream_t stream);
+
+/* du = bf16(scale * dy @ lora_B).  Replaces the autograd backward of `lora_B` (+ `* scaling`). */
+int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, void* du, int M, int N, int r,
+                    cudaStream_t stream);
+
+/* dx = dy @ dequant(W) + du @ lora_A  in one kernel (same decode, W consumed as an MN-major
+ * operand, no transposed or bf16 copy of W).  du may be NULL (base only).
+ * Replaces `MatMul4Bit.backward` (second dequantize_4bit + cuBLAS) plus the backward of
+ * `lora_A` and the gradient add. */
+int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A, void* dx, int M,
+                     int N, int K, int r, cudaStream_t stream);
+
+/* dA[r,K] (+)= du^T @ xd ;  dB[N,r] (+)= scale * dy^T @ u   (bf16 outputs, fp32 split-M partials
+ * in `workspace`, reduced in a fixed order).  dA / dB may point into flat gradient buckets.
+ * Replaces the weight-gradient halves of the autograd backward of `lora_A` / `lora_B`. */
+size_t b2q_lora_grads_workspace_bytes(int M, int N, int K, int r);
+int b2q_lora_grads(const void* dy, const void* xd, const void* u, const void* du, float scale, void* dA, void* dB,
+                   int accumulate, void* workspace, size_t workspace_bytes, int M, int N, int K, int r,
+                   cudaStream_t stream);
+
+/* Generic bf16 GEMM on the same tcgen05 pipeline: d[M,N] = alpha * a[M,K] @ b[K,N] with b given
+ * row-major [K,N] (b_is_kn = 1) or as [N,K] (b_is_kn = 0).  Used for du @ lora_A when dropout
+ * forbids fusing it into the dx kernel. */
+int b2q_gemm_bf16(const void* a, const void* b, int b_is_kn, float alpha, void* d, int M, int N, int K,
+                  cudaStream_t stream);
+
+/* dst_bf16[i] = bf16((accumulate ? dst[i] : 0) + scale * sum_s partial[s*n + i]) */
+int b2q_reduce_partials(const float* partial, int splits, int64_t n, float scale, void* out_bf16, int accumulate,
+                        cudaStream_t stream);
+
+/* Tuning hook: tile configuration of the two main kernels (0: 1 CTA, 128x128; 1: 1 CTA, 256x128;
+ * 2: CTA pair, 256x256; 3: CTA pair, 512x256 [default]); -1 keeps the default / B2Q_*_VARIANT env. */
+int b2q_set_variant(int fwd_variant, int dx_variant);
+
+/* Launch counter (every kernel this library launches increments it); for bench.py's gpu_launches. */
+uint64_t b2q_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2Q_H_ */
