@@ -1,0 +1,114 @@
+"""Autograd glue: the two ``torch.autograd.Function``s that put the C-ABI kernels behind modules.
+
+``MatMul4Bit``   stands in for ``bitsandbytes.autograd._functions.MatMul4Bit`` (frozen NF4 base
+                 only): forward ``Y = X W^T``, backward ``dX = dY W``, no dW.
+``QLoRALinear``  base + one active LoRA adapter, everything the PEFT wrapper's forward and
+                 its autograd backward compute in five
+                 launches forward+backward instead of ~25.
+
+Saved for backward: ``x`` (the caller's own tensor), ``u = xd A^T`` [M,r] and the dropout
+seed -- never a decoded weight, like bitsandbytes which saves only the packed bytes.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import functional as F
+
+
+def _flatten(x: torch.Tensor):
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype != torch.bfloat16:
+        x2 = x2.to(torch.bfloat16)
+    return x2.contiguous(), lead
+
+
+class MatMul4Bit(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, packed, qs):
+        x2, lead = _flatten(x)
+        ctx.qs = qs
+        ctx.lead = lead
+        ctx.in_dtype = x.dtype
+        ctx.save_for_backward(packed)
+        y = F.qlora_fwd(x2, packed, qs, None, None)
+        return y.reshape(*lead, y.shape[-1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        (packed,) = ctx.saved_tensors
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dy2, _ = _flatten(dy)
+            dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, None, None).reshape(*ctx.lead, -1).to(ctx.in_dtype)
+        return dx, None, None
+
+
+def matmul_4bit(x: torch.Tensor, weight: torch.Tensor, quant_state: F.QuantState,
+                bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``bnb.matmul_4bit(x, W.t(), bias, quant_state)`` equivalent (``weight`` is the packed tensor)."""
+    y = MatMul4Bit.apply(x, weight.data if isinstance(weight, torch.nn.Parameter) else weight, quant_state)
+    if bias is not None:
+        y = y + bias.to(y.dtype)
+    return y
+
+
+class QLoRALinear(torch.autograd.Function):
+    """y = x W^T + s * (drop(x) A^T) B^T  with dX, dA, dB.
+
+    ``grad_sink``: optional ``(dA_view, dB_view, accumulate)`` -- when given, the LoRA gradients
+    are written by the kernels straight into those (bucket) views and ``None`` is returned to
+    autograd for A and B (the data-parallel gradient sync owns them; see parallel.py).
+    """
+
+    @staticmethod
+    def forward(ctx, x, packed, qs, A, B, scale, p, seed, grad_sink):
+        x2, lead = _flatten(x)
+        a = A if A.dtype == torch.bfloat16 else A.to(torch.bfloat16)
+        b = B if B.dtype == torch.bfloat16 else B.to(torch.bfloat16)
+        a = a.contiguous()
+        b = b.contiguous()
+        xd = F.dropout_apply(x2, seed, p) if p > 0.0 else x2
+        u, us = F.lora_down(xd, a, scale)
+        y = F.qlora_fwd(x2, packed, qs, us, b)
+        ctx.qs, ctx.lead, ctx.in_dtype = qs, lead, x.dtype
+        ctx.scale, ctx.p, ctx.seed, ctx.grad_sink = float(scale), float(p), int(seed), grad_sink
+        ctx.param_dtypes = (A.dtype, B.dtype)
+        ctx.save_for_backward(x2, packed, a, b, u)
+        return y.reshape(*lead, y.shape[-1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, packed, a, b, u = ctx.saved_tensors
+        dy2, _ = _flatten(dy)
+        need_x, need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        du = F.lora_bwd_du(dy2, b, ctx.scale)
+        dx = None
+        if need_x:
+            if ctx.p > 0.0:
+                dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, None, None)
+                dxl = F.gemm_bf16(du, a, True)
+                F.dropout_bwd_add_(dx, dxl, ctx.seed, ctx.p)
+            else:
+                dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, du, a)
+            dx = dx.reshape(*ctx.lead, -1).to(ctx.in_dtype)
+        dA = dB = None
+        if need_a or need_b:
+            xd = F.dropout_apply(x2, ctx.seed, ctx.p) if ctx.p > 0.0 else x2
+            if ctx.grad_sink is not None:
+                dA_v, dB_v, acc = ctx.grad_sink
+                F.lora_grads(dy2, xd, u, du, ctx.scale, dA_v, dB_v, accumulate=acc)
+            else:
+                dA = torch.empty_like(a)
+                dB = torch.empty_like(b)
+                F.lora_grads(dy2, xd, u, du, ctx.scale, dA, dB, accumulate=False)
+                dA = dA.to(ctx.param_dtypes[0]) if need_a else None
+                dB = dB.to(ctx.param_dtypes[1]) if need_b else None
+        return dx, None, None, dA, dB, None, None, None, None
+
+
+def qlora_linear(x, packed, qs, A, B, scale: float, p: float = 0.0, seed: int = 0, grad_sink=None):
+    return QLoRALinear.apply(x, packed, qs, A, B, scale, p, seed, grad_sink)

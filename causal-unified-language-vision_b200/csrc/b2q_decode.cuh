@@ -16,6 +16,14 @@
 
 namespace b2q {
 
+// Raw PTX prmt (default mode).  NOT __byte_perm: that intrinsic ANDs the selector with 0x7777,
+// which would strip the sign-replicate bit (selector nibble bit 3) the mask generation relies on.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 struct Nf4Lut {
     uint32_t L[4];  // low bytes of entries 0..15  (entry e in byte e%4 of L[e/4])
     uint32_t H[4];  // high bytes
@@ -34,8 +42,8 @@ __device__ __forceinline__ void nf4_build_lut(const float (&code16)[16], float a
         P[j] = pack_bf16x2(__fmul_rn(code16[2 * j], absmax), __fmul_rn(code16[2 * j + 1], absmax));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        lut.L[j] = __byte_perm(P[2 * j], P[2 * j + 1], 0x6420);
-        lut.H[j] = __byte_perm(P[2 * j], P[2 * j + 1], 0x7531);
+        lut.L[j] = prmt(P[2 * j], P[2 * j + 1], 0x6420);
+        lut.H[j] = prmt(P[2 * j], P[2 * j + 1], 0x7531);
     }
 }
 
@@ -49,16 +57,16 @@ __device__ __forceinline__ void nf4_decode_word(uint32_t w, const Nf4Lut& lut, u
         const uint32_t s7 = h ? (w7 >> 16) : w7;
         const uint32_t x = h ? (w >> 16) : w;
         const uint32_t y = h ? (w >> 12) : (w << 4);
-        const uint32_t la = __byte_perm(lut.L[0], lut.L[1], s7);
-        const uint32_t lb = __byte_perm(lut.L[2], lut.L[3], s7);
-        const uint32_t ha = __byte_perm(lut.H[0], lut.H[1], s7);
-        const uint32_t hb = __byte_perm(lut.H[2], lut.H[3], s7);
+        const uint32_t la = prmt(lut.L[0], lut.L[1], s7);
+        const uint32_t lb = prmt(lut.L[2], lut.L[3], s7);
+        const uint32_t ha = prmt(lut.H[0], lut.H[1], s7);
+        const uint32_t hb = prmt(lut.H[2], lut.H[3], s7);
         // byte i of m = 0xFF iff bit 3 of nibble p_i is set (sign-replicate mode of PRMT)
-        const uint32_t m = __byte_perm(x, y, 0x9D8C);
+        const uint32_t m = prmt(x, y, 0x9D8C);
         const uint32_t lo = (la & ~m) | (lb & m);
         const uint32_t hi = (ha & ~m) | (hb & m);
-        out[2 * h + 0] = __byte_perm(lo, hi, 0x4051);
-        out[2 * h + 1] = __byte_perm(lo, hi, 0x6273);
+        out[2 * h + 0] = prmt(lo, hi, 0x4051);
+        out[2 * h + 1] = prmt(lo, hi, 0x6273);
     }
 }
 

@@ -20,6 +20,7 @@ reference only through cullavo/load_cullavo.py:73-82,86):
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 # The 16 NF4 code values (index = nibble), fp32.  QLoRA construction: quantiles of
 # N(0,1), asymmetric, normalised to [-1, 1]  (checked in tests/test_oracle.py).
@@ -85,19 +86,19 @@ def create_dynamic_map(signed: bool = True, max_exponent_bits: int = 7, total_bi
             fraction_items = int(2 ** (i + non_sign_bits - max_exponent_bits) + 1)
         else:
             fraction_items = int(2 ** (i + non_sign_bits - max_exponent_bits + 1) + 1)
-        boundaries = np.linspace(0.1, 1, fraction_items, dtype=np.float64).astype(np.float32)
-        means = ((boundaries[:-1] + boundaries[1:]) / np.float32(2.0)).astype(np.float32)
+        boundaries = torch.linspace(0.1, 1, fraction_items)  # fp32, as upstream
+        means = (boundaries[:-1] + boundaries[1:]) / 2.0
         scale = 10 ** (-(max_exponent_bits - 1) + i)
-        data += [scale * float(m) for m in means]
+        data += (scale * means).tolist()
         if signed:
-            data += [-(scale) * float(m) for m in means]
+            data += (-(scale) * means).tolist()
     if additional_items > 0:
-        boundaries = np.linspace(0.1, 1, additional_items + 1, dtype=np.float64).astype(np.float32)
-        means = ((boundaries[:-1] + boundaries[1:]) / np.float32(2.0)).astype(np.float32)
+        boundaries = torch.linspace(0.1, 1, additional_items + 1)
+        means = (boundaries[:-1] + boundaries[1:]) / 2.0
         scale = 10 ** (-(max_exponent_bits - 1) + i)
-        data += [scale * float(m) for m in means]
+        data += (scale * means).tolist()
         if signed:
-            data += [-(scale) * float(m) for m in means]
+            data += (-(scale) * means).tolist()
     data.append(0.0)
     data.append(1.0)
     assert len(data) == 2**total_bits

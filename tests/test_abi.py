@@ -1,0 +1,49 @@
+"""The C-ABI library builds, loads, and exports every symbol include/b2q.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b2q.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2q_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_path():
+    syms = _declared_symbols()
+    for must in ("b2q_nf4_decode", "b2q_nf4_quantize", "b2q_qlora_fwd", "b2q_qlora_bwd_dx", "b2q_lora_grads",
+                 "b2q_lora_down", "b2q_lora_bwd_du"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    for s in _declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/b2q.h but not exported by libb2q.so"
+
+
+def test_python_binding_covers_header(lib_built):
+    import b200qlora as q
+
+    lib = q._lib.load()
+    assert lib.b2q_version() == 100
+    assert set(_declared_symbols()) == set(q._lib.SIGNATURES), "ctypes signatures out of sync with include/b2q.h"
+    assert b"shape" in lib.b2q_error_string(-1)
+
+
+def test_sass_is_blackwell_native(lib_built):
+    """tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, TMA -> UTMALDG must be in the built library."""
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None:
+        import pytest
+
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", lib_built], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "PRMT"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass  # no legacy mma.sync path

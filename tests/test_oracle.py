@@ -1,0 +1,176 @@
+"""Known-answer tests that pin the CPU oracle (SURVEY.md section 8c list; none exist upstream)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import nf4
+from oracle.qlora import make_case, qlora_linear_fwd_bwd, rel_err
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_nf4_table_is_the_qlora_construction():
+    # (1) table identity: quantiles of N(0,1), 8 positive + 7 negative + 0, normalised (bnb create_normal_map)
+    from scipy.stats import norm
+
+    off = 0.9677083
+    v1 = norm.ppf(torch.linspace(off, 0.5, 9)[:-1]).tolist()
+    v3 = (-norm.ppf(torch.linspace(off, 0.5, 8)[:-1])).tolist()
+    v = torch.Tensor(v1 + [0] + v3).sort().values
+    v /= v.max()
+    assert np.array_equal(v.numpy(), nf4.NF4_CODE)
+
+
+def test_thresholds_are_midpoints():
+    mid = (nf4.NF4_CODE[1:].astype(np.float64) + nf4.NF4_CODE[:-1].astype(np.float64)) / 2
+    assert np.abs(mid - nf4.NF4_THRESHOLDS.astype(np.float64)).max() < 6e-8
+
+
+def test_dynamic_map():
+    c = nf4.create_dynamic_map()
+    assert c.shape == (256,) and c.dtype == np.float32
+    assert (np.diff(c) > 0).all()
+    assert c[-1] == 1.0 and abs(c[0] + 0.99296875) < 1e-6 and (c == 0).sum() == 1
+
+
+@pytest.mark.parametrize("a", [1.0, 0.02, 3.7e-3, 123.456])
+def test_code_values_round_trip(a):
+    # (2) decode(quantise(NF4[j] * a)) == bf16_rn(NF4[j] * a) for all 16 codes
+    w = np.zeros(64, np.float32)
+    w[:16] = nf4.NF4_CODE * np.float32(a)
+    st = nf4.quantize_nf4(w, 64, False)
+    assert st["absmax"][0] == np.float32(a)
+    codes = nf4.unpack_codes(st["packed"], 64)
+    assert list(codes[:16]) == list(range(16))
+    bits = nf4.dequantize_nf4(st)
+    assert np.array_equal(bits[:16], nf4.bf16_round(nf4.NF4_CODE * np.float32(a)))
+
+
+def test_nibble_order_even_element_high():
+    # (3) weights [NF4[15], NF4[0], ...] -> first byte 0xF0
+    w = np.zeros(64, np.float32)
+    w[0], w[1], w[2], w[3] = 1.0, -1.0, nf4.NF4_CODE[3], nf4.NF4_CODE[12]
+    st = nf4.quantize_nf4(w, 64, False)
+    assert st["packed"][0] == 0xF0 and st["packed"][1] == 0x3C
+
+
+def test_threshold_edges_go_down():
+    # (4) a value exactly on a mid-point maps to the lower code (strict >)
+    w = np.zeros(64, np.float32)
+    w[0] = 1.0  # absmax = 1 so normalised value == value
+    w[1:16] = nf4.NF4_THRESHOLDS
+    w[16:31] = np.nextafter(nf4.NF4_THRESHOLDS, np.float32(2.0))
+    codes = nf4.unpack_codes(nf4.quantize_nf4(w, 64, False)["packed"], 64)
+    assert list(codes[1:16]) == list(range(15))
+    assert list(codes[16:31]) == list(range(1, 16))
+
+
+def test_all_zero_block():
+    # (5) all-zero block -> codes 0, absmax 0, decode compares equal to 0
+    w = np.zeros(128, np.float32)
+    w[64:] = 0.5
+    st = nf4.quantize_nf4(w, 64, False)
+    assert st["absmax"][0] == 0 and (nf4.unpack_codes(st["packed"], 128)[:64] == 0).all()
+    assert (nf4.dequantize_nf4(st, as_bits=False)[:64] == 0).all()
+
+
+def test_double_quant_op_order_and_bound():
+    # (6) nested absmax = fl32(fl32(code256[q]*absmax2) + offset); error bound of the 8-bit code
+    rng = np.random.default_rng(0)
+    W = rng.normal(0, 0.02, (256, 1024)).astype(np.float32)
+    st = nf4.quantize_nf4(W, 64, True)
+    plain = nf4.quantize_nf4(W, 64, False)
+    assert np.array_equal(st["packed"], plain["packed"])
+    am = nf4.dequantize_absmax(st)
+    q, j = st["absmax_q"], np.arange(st["absmax_q"].size) // 256
+    manual = (st["code256"][q] * st["absmax2"][j]).astype(np.float32) + st["offset"]
+    assert np.array_equal(am, manual.astype(np.float32))
+    fused = (st["code256"][q].astype(np.float64) * st["absmax2"][j].astype(np.float64) + float(st["offset"]))
+    assert not np.array_equal(am, fused.astype(np.float32)) or True  # documents: no FMA contraction assumed
+    assert np.abs(am - plain["absmax"]).max() <= 0.02 * np.abs(plain["absmax"] - st["offset"]).max() + 1e-7
+
+
+def test_bf16_round_matches_torch():
+    x = np.random.default_rng(1).normal(0, 1, 4096).astype(np.float32)
+    ours = nf4.bf16_round(x).astype(np.int16)
+    theirs = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy()
+    assert np.array_equal(ours, theirs)
+
+
+def test_lora_b_zero_is_base_only():
+    # (7) B = 0 -> output equals base output bit for bit and dA = 0
+    case = make_case(32, 64, 128, 16, seed=3, lora_b_zero=True)
+    o = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], 0.25, case["dy"], mode="bf16")
+    W = torch.from_numpy(nf4.dequantize_nf4(case["state"], as_bits=False).copy())
+    base = (case["x"].float() @ W.t()).bfloat16().float()
+    assert torch.equal(o["y"], base)
+    assert float(o["dA"].abs().max()) == 0.0
+
+
+def test_fp64_autograd_agrees_with_explicit_backward():
+    # (8) gradcheck-style: the explicit backward formulas equal autograd of the forward in fp64
+    case = make_case(8, 64, 64, 8, seed=4, p=0.25, dtype=torch.float32)
+    W = torch.from_numpy(nf4.dequantize_nf4(case["state"], as_bits=False).copy()).double()
+    x = case["x"].double().requires_grad_(True)
+    A = case["A"].double().requires_grad_(True)
+    B = case["B"].double().requires_grad_(True)
+    mask = case["mask"].double()
+    s, p = 0.25, 0.25
+    y = x @ W.t() + s * (((x * mask / (1 - p)) @ A.t()) @ B.t())
+    dy = case["dy"].double()
+    y.backward(dy)
+    o = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], s, case["dy"], case["mask"], p, "fp32")
+    assert rel_err(o["y"], y.detach()) < 1e-5
+    assert rel_err(o["dx"], x.grad) < 1e-5
+    assert rel_err(o["dA"], A.grad) < 1e-5
+    assert rel_err(o["dB"], B.grad) < 1e-5
+
+
+def test_bf16_mode_within_tolerance_of_fp32():
+    case = make_case(64, 128, 256, 16, seed=5)
+    a = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], 0.25, case["dy"], mode="bf16")
+    b = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], 0.25, case["dy"], mode="fp32")
+    for k in ("y", "dx", "dA", "dB"):
+        assert rel_err(a[k], b[k]) < 2e-2, k
+
+
+def test_dp_mean_of_rank_grads_equals_full_batch():
+    # (10) mean over ranks of per-rank grads (each with dy scaled as a mean loss would) == single-process grad
+    case = make_case(64, 64, 128, 8, seed=6, dtype=torch.float32)
+    full = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], 0.25, case["dy"], mode="fp32")
+    parts = []
+    for r in range(2):
+        sl = slice(r * 32, (r + 1) * 32)
+        parts.append(qlora_linear_fwd_bwd(case["x"][sl], case["state"], case["A"], case["B"], 0.25,
+                                          case["dy"][sl] * 2.0, mode="fp32"))
+    mean_dA = (parts[0]["dA"] + parts[1]["dA"]) / 2
+    assert rel_err(mean_dA, full["dA"]) < 1e-5
+
+
+def test_golden_vectors():
+    """Committed fixtures (tests/golden/, made by oracle/make_golden.py) pin the oracle against drift."""
+    path = os.path.join(GOLDEN, "nf4_golden.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "nf4_golden.json")))
+    g = np.load(path)
+    for name, m in meta["cases"].items():
+        W = g[f"{name}.w"]
+        st = nf4.quantize_nf4(W, 64, m["double_quant"])
+        assert np.array_equal(st["packed"], g[f"{name}.packed"]), name
+        assert np.array_equal(nf4.dequantize_nf4(st), g[f"{name}.decoded_bits"]), name
+        if m["double_quant"]:
+            assert np.array_equal(st["absmax_q"], g[f"{name}.absmax_q"]), name
+            assert np.array_equal(st["absmax2"], g[f"{name}.absmax2"]), name
+            assert np.float32(st["offset"]) == g[f"{name}.offset"], name
+        else:
+            assert np.array_equal(st["absmax"], g[f"{name}.absmax"]), name
+    lin = meta["linear"]
+    case = make_case(lin["M"], lin["N"], lin["K"], lin["r"], seed=lin["seed"], double_quant=True)
+    o = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], lin["scale"], case["dy"], mode="bf16")
+    for k in ("y", "dx", "dA", "dB"):
+        gold = torch.from_numpy(g[f"linear.{k}"]).view(torch.bfloat16).float()
+        # fp32 BLAS summation order may differ between hosts: allow one bf16 ulp of the largest value
+        assert rel_err(o[k], gold) <= 2.0 ** -7, k
