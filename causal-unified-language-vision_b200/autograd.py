@@ -59,9 +59,9 @@ def matmul_4bit(x: torch.Tensor, weight: torch.Tensor, quant_state: F.QuantState
 class QLoRALinear(torch.autograd.Function):
     """y = x W^T + s * (drop(x) A^T) B^T  with dX, dA, dB.
 
-    ``grad_sink``: optional ``(dA_view, dB_view, accumulate)`` -- when given, the LoRA gradients
-    are written by the kernels straight into those (bucket) views and ``None`` is returned to
-    autograd for A and B (the data-parallel gradient sync owns them; see parallel.py).
+    ``grad_sink``: optional ``parallel.GradSink`` -- when given, the LoRA gradients are written by
+    the kernels straight into its (bucket) views and ``None`` is returned to autograd for A and B
+    (the data-parallel gradient sync owns them; see parallel.py).
     """
 
     @staticmethod
@@ -99,8 +99,9 @@ class QLoRALinear(torch.autograd.Function):
         if need_a or need_b:
             xd = F.dropout_apply(x2, ctx.seed, ctx.p) if ctx.p > 0.0 else x2
             if ctx.grad_sink is not None:
-                dA_v, dB_v, acc = ctx.grad_sink
-                F.lora_grads(dy2, xd, u, du, ctx.scale, dA_v, dB_v, accumulate=acc)
+                sink = ctx.grad_sink
+                F.lora_grads(dy2, xd, u, du, ctx.scale, sink.dA, sink.dB, accumulate=sink.accumulate())
+                sink.ready()  # may launch the bucket's all-reduce on the comm stream
             else:
                 dA = torch.empty_like(a)
                 dB = torch.empty_like(b)

@@ -5,14 +5,18 @@
 //          + sum over tail k-blocks  A2[M, 64] * B2[64, N]      (LoRA tail, bf16 via TMA)
 //
 // Roles (one CTA per SM, or a CTA pair with cta_group::2):
-//   warp 0      TMA producer          warp 1      UMMA issuer (leader CTA only)
-//   warp 2      TMEM allocator        warps 4-7   epilogue (TMEM -> registers -> global)
-//   warps 8..   NF4 decode (B_DEC): packed bytes (TMA-staged smem) -> registers (LUT/PRMT)
-//               -> bf16 in the canonical 128B-swizzled UMMA operand layout in smem
+//   warp 0      TMA producer (A, TMA-fed B)   warp 1   UMMA issuer (leader CTA only)
+//   warp 2      TMEM allocator                warp 3   TMA producer of the packed-NF4 ring (B_DEC)
+//   warps 4-7   epilogue (TMEM -> registers -> global)
+//   warps 8..   NF4 decode (B_DEC), NG groups of BNC threads taking k-blocks round-robin:
+//               packed bytes (TMA-staged smem) -> registers (LUT/PRMT) -> bf16 in the canonical
+//               128B-swizzled UMMA operand layout in smem
 //
-// Shared memory per stage: A tile (MT x 128 rows x 64 k bf16), B tile (BNC rows x 64 k bf16),
-// packed-NF4 tile (BNC x 32 B).  A stage is released by tcgen05.commit when the MMAs that read
-// it have finished.  The bf16 weight only ever exists in shared memory.
+// Shared memory: STAGES x {A tile (MT x 128 rows x 64 k bf16), B tile (BNC rows x 64 k bf16)}
+// plus an independent, deeper ring of PST packed-NF4 tiles (BNC x 32 B) so the packed bytes are
+// in shared memory long before the decoded-B slot they go to is free.  An operand stage is
+// released by tcgen05.commit when the MMAs that read it have finished.  The bf16 weight only
+// ever exists in shared memory.
 //
 // Operand layouts (both 128B-swizzled, see b2q_ptx.cuh umma_desc_sw128):
 //   K-major  tile [rows x 64 k]: row r at (r/8)*1024 + (r%8)*128, 16-byte chunk c at (c ^ (r%8))*16
@@ -53,8 +57,11 @@ struct GemmParams {
     int group_m;       // rasterisation: m-tiles per L2 slab
 };
 
-template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_>
+template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_, int NG_ = 2,
+          int PST_ = 6>
 struct GemmCfg {
+    static constexpr int NG = B_DEC_ ? NG_ : 0;   // decode groups (each BNC threads)
+    static constexpr int PST = B_DEC_ ? PST_ : 0; // packed-NF4 ring depth
     static constexpr int CG = CG_;          // CTAs per MMA (cta_group)
     static constexpr int MT = MT_;          // 128-row accumulators per CTA
     static constexpr int BN = BN_;          // UMMA N (whole pair)
@@ -69,23 +76,26 @@ struct GemmCfg {
     static constexpr int A_BYTES = MT * 128 * 64 * 2;
     static constexpr int B_BYTES = BNC * 64 * 2;
     static constexpr int P_BYTES = B_DEC ? BNC * 32 : 0;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + P_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES + PST * P_BYTES;
     static constexpr int ACC_COLS = MT * BN;
     static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS_RAW = ACC_COLS * ACC_STAGES;
     static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                      : TMEM_COLS_RAW <= 256 ? 256 : 512;
-    static constexpr int NDT = B_DEC ? BNC : 0;         // decode threads
-    static constexpr int NDW = NDT / 32;
-    static constexpr int THREADS = 256 + NDT;
+    static constexpr int NDT = B_DEC ? BNC : 0;         // decode threads per group
+    static constexpr int NDW = NDT / 32;                // decode warps per group (arrivals per stage)
+    static constexpr int THREADS = 256 + NG * NDT;
     static constexpr int BAR_BYTES = 1024;              // barriers + tmem ptr + code256
     static constexpr int CODE256_BYTES = B_DEC ? 1024 : 0;
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES + CODE256_BYTES;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + BAR_BYTES + CODE256_BYTES;
 
     static_assert(BN % (16 * CG) == 0 && BN <= 256, "UMMA N");
     static_assert(ACC_COLS <= 512, "TMEM columns");
     static_assert(!B_DEC || (BNC % 64 == 0), "decode tile");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+    static_assert(NG == 0 || NG == 1 || NG == 2 || NG == 4, "decode groups");
+    static_assert(THREADS <= 1024, "block size");
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& mt, int& nt, int& split) {
@@ -110,20 +120,23 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    constexpr int PST = Cfg::PST, NG = Cfg::NG;
+    const uint32_t bar_base = smem_base + Cfg::RING_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto pk_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + ACC_STAGES + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 2 * ACC_STAGES);
-    volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 2 * ACC_STAGES));
-    float* code256_s = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a); };
+    auto pk_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + s); };
+    auto pk_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + PST + s); };
+    constexpr int NBARS = 2 * STAGES + 2 * ACC_STAGES + 2 * PST;
+    static_assert(8 * NBARS + 8 <= Cfg::BAR_BYTES, "barrier area");
+    const uint32_t tmem_slot = bar_base + 8u * NBARS;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + 8 * NBARS);
+    float* code256_s = reinterpret_cast<float*>(smem_gen + Cfg::RING_BYTES + Cfg::BAR_BYTES);
 
     auto a_stage = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
     auto b_stage = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
-    auto p_stage = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + Cfg::B_BYTES; };
+    auto p_stage = [&](int s) { return smem_base + STAGES * Cfg::STAGE_BYTES + s * Cfg::P_BYTES; };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -146,7 +159,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), CG * (1 + Cfg::NDW));  // per CTA: producer (+tx) + one arrive per decode warp
             mbar_init(empty_bar(s), 1);                   // tcgen05.commit
-            mbar_init(pk_bar(s), 1);                      // producer (+tx)
+        }
+        for (int s = 0; s < PST; ++s) {
+            mbar_init(pk_bar(s), 1);                      // packed-ring producer (+tx)
+            mbar_init(pk_empty_bar(s), Cfg::NDW);         // decode warps, once the bytes are in registers
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
             mbar_init(tfull_bar(a), 1);                   // tcgen05.commit
@@ -214,16 +230,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
 #pragma unroll
                             for (int c = 0; c < BNC / 64; ++c) load(b_stage(s) + c * 8192, mapB, brow0 + c * 64, k0);
                         }
-                    } else {
-                        mbar_arrive_expect_tx(pk_bar(s), Cfg::P_BYTES);
-                        if constexpr (!Cfg::B_MN)
-                            tma_load_2d(p_stage(s), &p.tmB, pk_bar(s), k0 / 2, brow0);    // box 32 B x BNC rows of W
-                        else
-                            tma_load_2d(p_stage(s), &p.tmB, pk_bar(s), brow0 / 2, k0);    // box BNC/2 B x 64 rows of W
                     }
-                    // tail rounds: nothing to decode, but pk_bar must advance one phase per ring
-                    // round so the decode warps' parity stays in lockstep with the ring
-                    if (Cfg::B_DEC && tail) mbar_arrive(pk_bar(s));
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -265,6 +272,28 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
                 if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+            }
+        }
+    } else if (Cfg::B_DEC && warp == 3) {
+        // ================================== TMA producer, packed-NF4 ring ====
+        if (lane == 0) {
+            int ps = 0;
+            uint32_t pph = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                int mt_i, nt_i, split;
+                tile_coords(p, tile, mt_i, nt_i, split);
+                const int brow0 = nt_i * BN + static_cast<int>(rank) * BNC;
+                const int kb0 = split * p.kb_main;
+                for (int kb = 0; kb < p.kb_main; ++kb) {
+                    const int k0 = (kb0 + kb) * 64;
+                    mbar_wait(pk_empty_bar(ps), pph ^ 1u);
+                    mbar_arrive_expect_tx(pk_bar(ps), Cfg::P_BYTES);
+                    if constexpr (!Cfg::B_MN)
+                        tma_load_2d(p_stage(ps), &p.tmB, pk_bar(ps), k0 / 2, brow0);   // box 32 B x BNC rows of W
+                    else
+                        tma_load_2d(p_stage(ps), &p.tmB, pk_bar(ps), brow0 / 2, k0);   // box BNC/2 B x 64 rows of W
+                    if (++ps == PST) { ps = 0; pph ^= 1u; }
+                }
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -333,9 +362,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             }
             if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
         }
-    } else if (Cfg::B_DEC && warp >= 8) {
+    } else if (warp >= 8) {
+      if constexpr (Cfg::B_DEC) {
         // ======================================================= NF4 decode ====
-        const int t = threadIdx.x - 256;  // one thread = one quantisation block per stage
+        // NG groups of BNC threads; group g takes ring positions it with it % NG == g.  One thread
+        // = one quantisation block (64 weights, one absmax, one 128-byte operand row) per stage.
+        const int g = (threadIdx.x - 256) / Cfg::NDT;
+        const int t = (threadIdx.x - 256) % Cfg::NDT;
         float code16[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) code16[i] = __ldg(p.code16 + i);
@@ -352,34 +385,40 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         const uint32_t dst_off = Cfg::B_MN ? static_cast<uint32_t>((part * 8 + (r_loc >> 3)) * 1024 + (r_loc & 7) * 128)
                                            : static_cast<uint32_t>((r_loc >> 3) * 1024 + (r_loc & 7) * 128);
         const uint32_t key = static_cast<uint32_t>(r_loc & 7);
-        int s = 0;
-        uint32_t ph = 0;
+        uint32_t it = 0;   // ring position over all k-blocks (main + tail) of all tiles
+        uint32_t pit = 0;  // ring position over main k-blocks only (packed ring)
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
             int mt_i, nt_i, split;
             tile_coords(p, tile, mt_i, nt_i, split);
             const int n0 = nt_i * BN + static_cast<int>(rank) * BNC;
             // absmax block index of k-block kb:  K-major: (n0 + t) * kpr + kb
             //                                    MN-major: (kb*64 + r_loc) * kpr + (n0 + part*64)/64
-            long long blk = Cfg::B_MN ? static_cast<long long>(r_loc) * p.kpr + (n0 >> 6) + part
-                                      : static_cast<long long>(n0 + t) * p.kpr;
             const long long blk_step = Cfg::B_MN ? 64LL * p.kpr : 1LL;
-            blk += static_cast<long long>(split) * p.kb_main * blk_step;
-            float a_next = p.kb_main > 0 ? absmax_of(blk) : 0.f;
-            for (int kb = 0; kb < p.kb_main; ++kb) {
+            const long long blk0 = (Cfg::B_MN ? static_cast<long long>(r_loc) * p.kpr + (n0 >> 6) + part
+                                              : static_cast<long long>(n0 + t) * p.kpr) +
+                                   static_cast<long long>(split) * p.kb_main * blk_step;
+            // first main k-block of this tile that belongs to this group
+            int kb_first = static_cast<int>((static_cast<uint32_t>(g) - it) & (NG - 1));
+            float a_next = kb_first < p.kb_main ? absmax_of(blk0 + kb_first * blk_step) : 0.f;
+            for (int kb = kb_first; kb < p.kb_main; kb += NG) {
                 const float a = a_next;
-                blk += blk_step;
-                if (kb + 1 < p.kb_main) a_next = absmax_of(blk);  // prefetch one k-block ahead
+                if (kb + NG < p.kb_main) a_next = absmax_of(blk0 + (kb + NG) * blk_step);  // prefetch
                 Nf4Lut lut;
                 nf4_build_lut(code16, a, lut);
-                mbar_wait(pk_bar(s), ph);
+                const uint32_t pi = pit + kb, ps = pi % PST, pph = (pi / PST) & 1u;
+                mbar_wait(pk_bar(ps), pph);
                 uint32_t w[8];
                 {
-                    const uint32_t src = p_stage(s) + t * 32;
+                    const uint32_t src = p_stage(ps) + t * 32;
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src));
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                                  : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(src + 16));
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pk_empty_bar(ps));  // packed slot may be refilled
+                const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);              // decoded-B slot free (MMAs that read it retired)
                 const uint32_t dst = b_stage(s) + dst_off;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -393,17 +432,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 if (lane == 0) {
                     if constexpr (CG == 2) mbar_arrive_cluster(full_bar_arrive(s)); else mbar_arrive(full_bar(s));
                 }
-                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
-            for (int kb = 0; kb < p.kb_tail; ++kb) {  // LoRA tail: B arrives by TMA, just keep the count
-                mbar_wait(pk_bar(s), ph);
+            // LoRA tail k-blocks: B arrives by TMA; the group that owns the ring position keeps the count
+            for (int kb = p.kb_main; kb < kb_total; ++kb) {
+                const uint32_t si = it + kb;
+                if ((si & (NG - 1)) != static_cast<uint32_t>(g)) continue;
+                const uint32_t s = si % STAGES, ph = (si / STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
                 __syncwarp();
                 if (lane == 0) {
                     if constexpr (CG == 2) mbar_arrive_cluster(full_bar_arrive(s)); else mbar_arrive(full_bar(s));
                 }
-                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
+            it += kb_total;
+            pit += p.kb_main;
         }
+      }
     }
 
     // ------------------------------------------------------------- teardown ----

@@ -151,7 +151,7 @@ class LoraLinear4bit(nn.Module, LoraLayer):
         LoraLayer.__init__(self, base_layer)
         self._active_adapter = adapter_name
         self.update_layer(adapter_name, r, lora_alpha, lora_dropout, init_lora_weights)
-        self._grad_sinks = {}  # adapter -> (dA_view, dB_view); installed by parallel.GradSync
+        self._grad_sinks = {}  # adapter -> parallel.GradSync (owns the flat gradient buckets)
 
     # PEFT exposes these on the wrapper as well
     @property
@@ -181,8 +181,7 @@ class LoraLinear4bit(nn.Module, LoraLayer):
         seed = int(torch.randint(0, 2**62, (1,)).item()) if p > 0.0 else 0
         sink = None
         if name in self._grad_sinks and torch.is_grad_enabled():
-            dA_v, dB_v, state = self._grad_sinks[name]
-            sink = (dA_v, dB_v, state.accumulate_flag(self, name))
+            sink = self._grad_sinks[name].sink_for(self)  # parallel.GradSync: grads go straight into its buckets
         inp_dtype = x.dtype
         y = qlora_linear(x, base.weight.data, qs, A, B, self.scaling[name], p, seed, sink)
         if base.bias is not None:

@@ -1,0 +1,180 @@
+"""Data-parallel LoRA-gradient sync: flat buckets + NCCL all-reduce(mean) overlapped with backward.
+
+What it replaces: the DDP reducer that ``accel.prepare`` installs
+(/root/reference/trainer/utils_trainer.py:32-37) and ``accel.backward`` is meant to drive
+(/root/reference/trainer/default_trainer.py:83-84).  The reference unwraps ``.module`` right
+after ``prepare`` (utils_trainer.py:37), which disarms DDP's reducer, and adds a full barrier
+between forward and backward (/root/reference/pipeline/CuLLaVOPipeline.py:87); this module
+implements the INTENDED semantics -- mean-reduced gradients every step -- and no barrier
+(deviation recorded in DESIGN.md).
+
+Design (one process per GPU, weights replicated, batch sharded):
+  * every trainable LoRA ``A [r,K]`` / ``B [N,r]`` gets a view into a flat bucket, assigned in
+    REVERSE forward order (the order backward produces them); ``param.grad`` is that view;
+  * the backward kernels (``b2q_lora_grads``) write dA / dB straight into the views -- no
+    autograd accumulation pass, no flatten / unflatten copies;
+  * when the last gradient of a bucket has been produced an event is recorded on the compute
+    stream, the comm stream waits on it and issues ONE ``all_reduce`` for the bucket
+    (NCCL over NVLink 5 / NVSwitch; ``ReduceOp.AVG``), overlapping the remaining backward;
+  * ``finish()`` makes the compute stream wait for the comm stream before the optimizer step.
+The same class runs on CPU tensors with the ``gloo`` backend (SUM then divide) for tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class GradSink:
+    """Where one module's LoRA gradients go; handed to ``autograd.QLoRALinear`` and consulted in backward."""
+
+    def __init__(self, dA: torch.Tensor, dB: torch.Tensor, accumulate: Callable[[], bool],
+                 on_ready: Optional[Callable[[], None]] = None):
+        self.dA, self.dB, self._accumulate, self._on_ready = dA, dB, accumulate, on_ready
+
+    def accumulate(self) -> bool:
+        return bool(self._accumulate())
+
+    def ready(self) -> None:
+        if self._on_ready is not None:
+            self._on_ready()
+
+
+@dataclass
+class _Bucket:
+    flat: torch.Tensor
+    members: List[int] = field(default_factory=list)  # slot ids
+    pending: int = 0
+    work: object = None
+
+
+class GradSync:
+    def __init__(self, modules: Sequence, adapter_name: str, process_group=None, bucket_bytes: int = 64 << 20,
+                 grad_dtype: torch.dtype = torch.bfloat16, install: bool = True):
+        """``modules``: the LoRA-wrapped linears in FORWARD order (``LoraLinear4bit`` or anything with
+        ``lora_A[adapter].weight`` / ``lora_B[adapter].weight``)."""
+        self.adapter = adapter_name
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.modules = list(modules)
+        self.grad_dtype = grad_dtype
+        params = []
+        for m in reversed(self.modules):  # backward order
+            params.append((m, m.lora_B[adapter_name].weight, "B"))
+            params.append((m, m.lora_A[adapter_name].weight, "A"))
+        if not params:
+            raise ValueError("no LoRA modules")
+        device = params[0][1].device
+        self.device = device
+        elem = torch.empty(0, dtype=grad_dtype).element_size()
+        # bucket assignment
+        plan, cur, cur_bytes = [], [], 0
+        for i, (_, prm, _) in enumerate(params):
+            nbytes = prm.numel() * elem
+            if cur and cur_bytes + nbytes > bucket_bytes:
+                plan.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(i)
+            cur_bytes += nbytes
+        if cur:
+            plan.append(cur)
+        self.buckets: List[_Bucket] = []
+        self._views = {}
+        self._slot_bucket = {}
+        for members in plan:
+            total = sum(params[i][1].numel() for i in members)
+            flat = torch.zeros(total, dtype=grad_dtype, device=device)
+            b = _Bucket(flat=flat, members=list(members))
+            off = 0
+            for i in members:
+                mod, prm, which = params[i]
+                # keep 16-byte alignment of every view (kernels use 128-bit accesses)
+                assert (off * elem) % 16 == 0
+                view = flat[off:off + prm.numel()].view_as(prm)
+                off += prm.numel()
+                self._views[(id(mod), which)] = view
+                self._slot_bucket[(id(mod), which)] = len(self.buckets)
+                if prm.dtype == grad_dtype:
+                    prm.grad = view
+            self.buckets.append(b)
+        self._written = set()
+        self._use_cuda = device.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=device) if self._use_cuda else None
+        self._done_events = []
+        if install:
+            for m in self.modules:
+                m._grad_sinks[adapter_name] = self
+        self.begin_step()
+
+    # ---- per step -----------------------------------------------------------------------
+    def begin_step(self) -> None:
+        """Call after ``zero_grad`` / before the first backward of an optimizer step."""
+        self._written.clear()
+        for b in self.buckets:
+            b.pending = len(b.members)
+            b.work = None
+        self._done_events = []
+
+    def sink_for(self, mod) -> GradSink:
+        """Gradient destination for ``mod`` in the coming backward (used by ``LoraLinear4bit.forward``)."""
+        key = id(mod)
+        return GradSink(self._views[(key, "A")], self._views[(key, "B")], lambda: key in self._written,
+                        lambda: self._ready(mod))
+
+    def _ready(self, mod) -> None:
+        key = id(mod)
+        first = key not in self._written
+        self._written.add(key)
+        if not first:
+            return
+        for which in ("A", "B"):
+            bi = self._slot_bucket[(key, which)]
+            b = self.buckets[bi]
+            b.pending -= 1
+            if b.pending == 0 and self.world > 1 and not self.defer:
+                self._launch(b)
+
+    defer = False  # True while accumulating micro-batches: reduce only on the last one
+
+    def _launch(self, b: _Bucket) -> None:
+        if self._use_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.group)
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+            self._done_events.append(done)
+        else:
+            dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group)
+            b.flat.div_(self.world)
+
+    def reduce_all(self) -> None:
+        """Reduce every bucket now (after the last micro-batch when ``defer`` was set)."""
+        if self.world > 1:
+            for b in self.buckets:
+                self._launch(b)
+
+    def finish(self) -> None:
+        """Order the optimizer step after every in-flight all-reduce."""
+        if self._use_cuda:
+            cur = torch.cuda.current_stream(self.device)
+            for ev in self._done_events:
+                cur.wait_event(ev)
+        self._done_events = []
+
+    # ---- helpers ------------------------------------------------------------------------
+    def zero_grad(self) -> None:
+        for b in self.buckets:
+            b.flat.zero_()
+        self.begin_step()
+
+    def grad_bytes(self) -> int:
+        return sum(b.flat.numel() * b.flat.element_size() for b in self.buckets)
+
+    def flat_grads(self) -> List[torch.Tensor]:
+        return [b.flat for b in self.buckets]

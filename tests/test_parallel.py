@@ -1,0 +1,88 @@
+"""Data-parallel gradient sync host logic on CPU: bucket layout + world_size-2 gloo all-reduce(mean)."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class FakeLora(nn.Module):
+    """Has the attribute surface GradSync needs (lora_A/lora_B ModuleDicts, _grad_sinks)."""
+
+    def __init__(self, n, k, r, name="a"):
+        super().__init__()
+        self.lora_A = nn.ModuleDict({name: nn.Linear(k, r, bias=False)})
+        self.lora_B = nn.ModuleDict({name: nn.Linear(r, n, bias=False)})
+        self._grad_sinks = {}
+
+
+def _mods():
+    torch.manual_seed(0)
+    return [FakeLora(64, 32, 8), FakeLora(32, 64, 8), FakeLora(128, 32, 8)]
+
+
+def test_bucket_layout_reverse_order_and_views():
+    par = importlib.import_module("causal-unified-language-vision_b200.parallel")
+    mods = _mods()
+    gs = par.GradSync(mods, "a", bucket_bytes=3000, grad_dtype=torch.float32)
+    assert len(gs.buckets) > 1
+    assert gs.grad_bytes() == sum(p.numel() * 4 for m in mods for p in m.parameters())
+    # first bucket starts with the LAST module's B (what backward produces first)
+    first = gs.buckets[0].flat
+    assert mods[-1].lora_B["a"].weight.grad.data_ptr() == first.data_ptr()
+    for m in mods:
+        assert m.lora_A["a"].weight.grad.shape == m.lora_A["a"].weight.shape
+        assert m._grad_sinks["a"] is gs
+    # writing through a sink lands in param.grad; the accumulate flag flips after the first write of a step
+    s = gs.sink_for(mods[0])
+    assert not s.accumulate()
+    s.dA.fill_(2.0)
+    s.ready()
+    assert gs.sink_for(mods[0]).accumulate()
+    assert float(mods[0].lora_A["a"].weight.grad.mean()) == 2.0
+    gs.begin_step()
+    assert not gs.sink_for(mods[0]).accumulate()
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = importlib.import_module("causal-unified-language-vision_b200.parallel")
+    mods = _mods()
+    gs = par.GradSync(mods, "a", bucket_bytes=3000, grad_dtype=torch.float32)
+    gs.begin_step()
+    for i, m in enumerate(reversed(mods)):  # backward order
+        s = gs.sink_for(m)
+        s.dA.fill_(float(rank + 1) * (i + 1))
+        s.dB.fill_(float(rank + 1) * 10 * (i + 1))
+        s.ready()
+    gs.finish()
+    out = [(float(m.lora_A["a"].weight.grad.mean()), float(m.lora_B["a"].weight.grad.mean())) for m in reversed(mods)]
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_allreduce_mean_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    # mean over ranks of (rank+1)*c = 1.5*c
+    for r in (0, 1):
+        for i, (a, b) in enumerate(res[r]):
+            assert abs(a - 1.5 * (i + 1)) < 1e-6 and abs(b - 15.0 * (i + 1)) < 1e-6
