@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the QLoRA linear-stack hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" = forward of all 224 QLoRA linears (32 layers x q/k/v/o/gate/up/down, NF4 base with
+double-quantised absmax + LoRA r=64, dropout 0.05) followed by backward of all (dX, dA, dB into
+flat buckets, all-reduced over NCCL when N > 1) on 8 x 2048 synthetic tokens per GPU
+(BASELINE.json configs[2]; configs[3] is the same per GPU at N=8).  Rank 0 prints ONE JSON line.
+
+  value     whole-job tokens/s, inputs resident in HBM, C-ABI ops called back to back
+  e2e       same metric through the module surface (LoraLinear4bit.forward + autograd), with the
+            step's activations copied host->device from pinned memory and the result read back
+  roofline  tensor-core roofline of the dominant kernel (NF4-decode tcgen05 GEMM, fwd + dX)
+  cpu_baseline / --impl reference   the CPU oracle (fp32 restatement of bitsandbytes + PEFT) on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "qlora_linear_stack_train_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"burst": float(d["bf16_tflops"]), "sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "hbm": float(d["hbm_gbs"]), "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every 200 ms while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_ev = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+            }
+            while not self._stop_ev.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+                self._stop_ev.wait(0.2)
+        except Exception as e:  # no NVML: leave the record empty rather than fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_sample(threads: int, iters: int = 3):
+    """One BASELINE-C1 linear (4096x4096 NF4 + LoRA r=64, 704 tokens) fwd+bwd in fp32 on the host, NF4 decode
+    in both passes as MatMul4Bit does.  Returns (seconds per iteration, flops per iteration)."""
+    import torch
+
+    from oracle.qlora import make_case, qlora_flops, qlora_linear_fwd_bwd
+
+    torch.set_num_threads(threads)
+    M, N, K, r = 704, 4096, 4096, 64
+    case = make_case(M, N, K, r, seed=0, double_quant=True, dtype=torch.float32)
+    ts = []
+    for i in range(iters + 1):
+        t0 = time.perf_counter()
+        qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], 0.25, case["dy"], mode="fp32")
+        if i > 0:
+            ts.append(time.perf_counter() - t0)
+    return statistics.median(ts), qlora_flops(M, N, K, r)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"{args.layers}-layer 7B QLoRA linear stack ({args.shapes}: q/k/v/o 4096, gate/up/down 4096x14336), "
+                    f"NF4 blocksize 64 + double-quant absmax, LoRA r={args.r} alpha=16 dropout={args.dropout}, "
+                    f"batch {args.batch} x seq {args.seq} per GPU, fwd+bwd (dX, dA, dB)",
+        "baseline_config": "configs[2]" if world == 1 else "configs[3]",
+        "layers": args.layers, "tokens_per_gpu": args.batch * args.seq, "global_tokens": args.batch * args.seq * world,
+        "rank_r": args.r, "dropout": args.dropout, "recompute": bool(args.recompute),
+        "parallelism": f"dp{world}", "cache": "inputs_exceed_l2 (4 GB packed weights + >=134 MB activations per launch)",
+    }
+
+
+def run_reference(args, world, rank):
+    """--impl reference: the CPU oracle on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from importlib import import_module
+
+    stack = import_module("causal-unified-language-vision_b200.stack")
+    threads = os.cpu_count() or 1
+    fpt = stack.stack_flops_per_token(stack.SHAPE_SETS[args.shapes], args.layers, args.r)
+    times = []
+    for i in range(args.warmup + args.steps):
+        sec, flops = cpu_oracle_sample(threads, iters=1)
+        if i >= args.warmup:
+            times.append(sec)
+    sec = statistics.mean(times)
+    toks = (flops / sec) / fpt
+    sample = ("one q_proj-shaped linear (4096x4096 NF4 double-quant + LoRA r=64), 704 tokens, fp32 fwd+bwd with the "
+              "NF4 decode in both passes; tokens/s of the full stack extrapolated linearly in FLOPs")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": toks, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": {"value": toks, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "gflops": flops / sec / 1e9},
+        "e2e": {"value": toks, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--seq", type=int, default=2048)
+    ap.add_argument("--r", type=int, default=64)
+    ap.add_argument("--dropout", type=float, default=0.05)
+    ap.add_argument("--shapes", default="mistral_literal")
+    ap.add_argument("--recompute", action="store_true", help="also re-run the forward inside backward (grad ckpt)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference "
+                         "for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import b200qlora as q
+
+    stackmod = import_module("causal-unified-language-vision_b200.stack")
+    F = q.functional
+    shapes = stackmod.SHAPE_SETS[args.shapes]
+    M = args.batch * args.seq
+    stack = stackmod.QLoRALinearStack(args.layers, shapes, M, r=args.r, dropout=args.dropout, device=dev, seed=0)
+    fpt = stack.flops_per_token()
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- per-launch timing of the dominant kernel (events on the launching stream) -------------
+    main_events, main_flops = [], [0.0]
+    orig_fwd, orig_dx = F.qlora_fwd, F.qlora_bwd_dx
+    timing_on = [False]
+
+    def timed(fn, flops_of):
+        def wrapper(*a):
+            if not timing_on[0]:
+                return fn(*a)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a)
+            e1.record()
+            main_events.append((e0, e1))
+            main_flops[0] += flops_of(*a)
+            return out
+        return wrapper
+
+    def fwd_flops(x, packed, qs, us, lora_b):
+        m, n, k = x.shape[0], int(qs.shape[0]), int(qs.shape[1])
+        return 2.0 * m * n * k + (0.0 if us is None else 2.0 * m * us.shape[1] * n)
+
+    def dx_flops(dy, packed, qs, du, lora_a):
+        m, n, k = dy.shape[0], int(qs.shape[0]), int(qs.shape[1])
+        return 2.0 * m * n * k + (0.0 if du is None else 2.0 * m * du.shape[1] * k)
+
+    F.qlora_fwd = timed(orig_fwd, fwd_flops)
+    F.qlora_bwd_dx = timed(orig_dx, dx_flops)
+
+    # ---- value: device-resident inputs, C-ABI ops back to back -------------------------------
+    for _ in range(args.warmup):
+        stack.step_direct(recompute=args.recompute)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = F.launch_count()
+    timing_on[0] = True
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        stack.step_direct(recompute=args.recompute)
+    t1.record()
+    barrier()
+    timing_on[0] = False
+    launches = F.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = M * world / (ms / 1e3)
+
+    kern_ms = sum(a.elapsed_time(b) for a, b in main_events)
+    n_main = len(main_events)
+    achieved = main_flops[0] / (kern_ms / 1e3) / 1e12 if kern_ms > 0 else 0.0
+    F.qlora_fwd, F.qlora_bwd_dx = orig_fwd, orig_dx
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "main_kernel_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_avg")
+
+    # ---- e2e: module surface + host buffers ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        widths_in = sorted({k for _, _, k in shapes})
+        widths_out = sorted({n for _, n, _ in shapes})
+        base_k, base_n = widths_in[0], widths_out[0]
+        host_x = stack.inputs[base_k].cpu().pin_memory()
+        host_dy = stack.grads_out[base_n].cpu().pin_memory()
+        host_out = torch.empty(1, dtype=torch.float32).pin_memory()
+        h2d = host_x.numel() * 2 + host_dy.numel() * 2
+
+        def widen(t, width):
+            reps = (width + t.shape[1] - 1) // t.shape[1]
+            return t if width == t.shape[1] else torch.cat([t] * reps, dim=1)[:, :width].contiguous()
+
+        def e2e_step():
+            x = host_x.to(dev, non_blocking=True)
+            dy = host_dy.to(dev, non_blocking=True)
+            ins = {k: widen(x, k) for k in widths_in}
+            gos = {n: widen(dy, n) for n in widths_out}
+            g2 = stack.step_modules(ins, gos)
+            host_out.copy_(g2.reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(host_out[0])
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": M * world / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ems, "api": "LoraLinear4bit.forward + autograd (QLoRALinear) -> C ABI"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sec, flops = cpu_oracle_sample(threads, iters=3)
+            cpu = {"value": (flops / sec) / fpt, "unit": UNIT, "cores": threads, "kind": "port",
+                   "gflops": flops / sec / 1e9,
+                   "sample": "one q_proj-shaped linear (4096x4096 NF4 double-quant + LoRA r=64), 704 tokens, fp32 "
+                             "fwd+bwd incl. NF4 decode in both passes (oracle/qlora.py); full-stack tokens/s "
+                             "extrapolated linearly in FLOPs"}
+        step_tflops = fpt * M / (ms / 1e3) / 1e12
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args, world),
+            "per_gpu_tokens_per_s": value / world,
+            "step_tflops_per_gpu": step_tflops,
+            "pct_bf16_tc_peak": {"of_measured_burst": step_tflops / peaks["burst"],
+                                 "of_measured_sustained": step_tflops / peaks["sustained"], "peaks": peaks["source"]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "qlora_gemm_kernel (NF4-decode tcgen05 GEMM, fwd + dX launches)",
+                         "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["sustained"], "traffic": traffic, "launches_timed": n_main,
+                         "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
+                         "share_of_step": kern_ms / (ms * args.steps) if ms > 0 else None},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
