@@ -40,6 +40,7 @@ class NF4Weight(ct.Structure):
 SIGNATURES = {
     "b2q_version": (c_int, []),
     "b2q_error_string": (ct.c_char_p, [c_int]),
+    "b2q_last_error_detail": (ct.c_char_p, []),
     "b2q_nf4_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_i64,
                                c_int, c_int, c_void_p]),
     "b2q_nf4_quantize": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p]),
@@ -87,4 +88,6 @@ def load() -> ct.CDLL:
 def check(code: int, what: str) -> None:
     if code != 0:
         msg = load().b2q_error_string(code)
-        raise RuntimeError(f"{what} failed: {msg.decode() if msg else code} (code {code})")
+        detail = load().b2q_last_error_detail() if code < 0 else b""
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else code} (code {code})"
+                           + (f" [{detail.decode()}]" if detail else ""))

@@ -9,6 +9,7 @@
 namespace b2q {
 
 std::atomic<uint64_t> g_launch_count{0};
+static char g_last_error[512] = "";
 
 // ---------------------------------------------------------------- tensor maps ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -33,17 +34,42 @@ static EncodeTiledFn get_encode_fn() {
 static int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t inner,
                        uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
     EncodeTiledFn fn = get_encode_fn();
-    if (fn == nullptr) return B2Q_ERR_DRIVER;
-    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0) return B2Q_ERR_ARG;
+    if (fn == nullptr) {
+        snprintf(g_last_error, sizeof(g_last_error), "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+        return B2Q_ERR_DRIVER;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0) {
+        snprintf(g_last_error, sizeof(g_last_error), "operand not 16-byte aligned (base %p, pitch %llu B)", base,
+                 static_cast<unsigned long long>(pitch_bytes));
+        return B2Q_ERR_ARG;
+    }
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {pitch_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     (void)elem_bytes;
-    CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : B2Q_ERR_DRIVER;
+    auto encode = [&]() {
+        return fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r = encode();
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        // Driver-API call on a thread where the runtime has not bound a context yet (e.g. the first op
+        // torch's autograd engine thread runs): bind the primary context of the current device, retry.
+        cudaFree(nullptr);
+        r = encode();
+    }
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_last_error, sizeof(g_last_error),
+                 "cuTensorMapEncodeTiled -> CUresult %d (base %p, dims {%llu,%llu}, pitch %llu B, box {%u,%u}, "
+                 "elem %d B, swizzle128 %d)",
+                 static_cast<int>(r), base, static_cast<unsigned long long>(inner),
+                 static_cast<unsigned long long>(outer), static_cast<unsigned long long>(pitch_bytes), box_inner,
+                 box_outer, elem_bytes, static_cast<int>(swizzle128));
+        return B2Q_ERR_DRIVER;
+    }
+    return 0;
 }
 
 // bf16 operand, K-major use: tensor [rows][kdim], box 64 k x box_rows.
@@ -148,6 +174,8 @@ using namespace b2q;
 extern "C" int b2q_version(void) { return B2Q_VERSION; }
 
 extern "C" uint64_t b2q_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" const char* b2q_last_error_detail(void) { return g_last_error; }
 
 extern "C" const char* b2q_error_string(int code) {
     switch (code) {

@@ -55,6 +55,8 @@ typedef struct b2q_nf4_weight {
 
 int b2q_version(void);
 const char* b2q_error_string(int code);
+/* Human-readable detail of the last B2Q_ERR_DRIVER / B2Q_ERR_ARG raised by a tensor-map encode. */
+const char* b2q_last_error_detail(void);
 
 /* ---- NF4 blockwise quantise / dequantise ------------------------------------------------ */
 

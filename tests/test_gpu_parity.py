@@ -91,15 +91,18 @@ def test_quantize_matches_oracle(F, cuda_dev, dq):
         assert np.array_equal(qs.absmax.cpu().numpy(), st["absmax"])
 
 
-def test_quantize_decode_round_trip_idempotent(F, cuda_dev):
-    """decode(quantise(decode(quantise(W)))) == decode(quantise(W)) at a full-size projection (size-independent property)."""
+def test_quantize_decode_round_trip_codes_stable(F, cuda_dev):
+    """Size-independent property at a full-size projection: re-quantising the decoded weight reproduces
+    the same 4-bit codes (the decoded values sit on the code points), and both decode paths agree."""
     W = torch.randn(4096, 4096, device=cuda_dev) * 0.02
     p1, q1 = F.quantize_4bit(W, compress_statistics=False)
     d1 = F.dequantize_4bit(p1, q1)
     p2, q2 = F.quantize_4bit(d1.float(), compress_statistics=False)
-    d2 = F.dequantize_4bit(p2, q2)
-    assert torch.equal(d1, d2)
+    assert torch.equal(p1, p2)
     assert torch.equal(F.dequantize_4bit(p1, q1, algo=0), F.dequantize_4bit(p1, q1, algo=1))
+    # |decode - W| <= absmax * (largest half-gap of the code book = 0.5*(1 - 0.6961928), codes 0/1) + bf16 rounding
+    am = q1.absmax.repeat_interleave(64).reshape(4096, 4096)
+    assert bool(((d1.float() - W).abs() <= am * 0.1520 + am * 2.0 ** -8 + 1e-12).all())
 
 
 CASES = [  # M, N, K, r, double_quant
