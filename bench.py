@@ -212,11 +212,11 @@ def main():
             return out
         return wrapper
 
-    def fwd_flops(x, packed, qs, us, lora_b):
+    def fwd_flops(x, packed, qs, us, lora_b, *rest):
         m, n, k = x.shape[0], int(qs.shape[0]), int(qs.shape[1])
         return 2.0 * m * n * k + (0.0 if us is None else 2.0 * m * us.shape[1] * n)
 
-    def dx_flops(dy, packed, qs, du, lora_a):
+    def dx_flops(dy, packed, qs, du, lora_a, *rest):
         m, n, k = dy.shape[0], int(qs.shape[0]), int(qs.shape[1])
         return 2.0 * m * n * k + (0.0 if du is None else 2.0 * m * du.shape[1] * k)
 

@@ -48,15 +48,16 @@ SIGNATURES = {
     "b2q_dropout_mask": (c_int, [c_void_p, c_i64, c_u64, c_float, c_void_p]),
     "b2q_dropout_apply": (c_int, [c_void_p, c_void_p, c_i64, c_u64, c_float, c_void_p]),
     "b2q_dropout_bwd_add": (c_int, [c_void_p, c_void_p, c_i64, c_u64, c_float, c_void_p]),
-    "b2q_lora_down": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b2q_lora_down": (c_int, [c_void_p, c_void_p, c_float, c_u64, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                              c_void_p]),
     "b2q_qlora_fwd": (c_int, [c_void_p, ct.POINTER(NF4Weight), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_int, c_void_p]),
     "b2q_lora_bwd_du": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "b2q_qlora_bwd_dx": (c_int, [c_void_p, ct.POINTER(NF4Weight), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                 c_int, c_void_p]),
+    "b2q_qlora_bwd_dx": (c_int, [c_void_p, ct.POINTER(NF4Weight), c_void_p, c_void_p, c_u64, c_float, c_void_p, c_int,
+                                 c_int, c_int, c_int, c_void_p]),
     "b2q_lora_grads_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "b2q_lora_grads": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p,
-                               c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2q_lora_grads": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_u64, c_float, c_void_p, c_void_p,
+                               c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "b2q_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2q_reduce_partials": (c_int, [c_void_p, c_int, c_i64, c_float, c_void_p, c_int, c_void_p]),
     "b2q_set_variant": (c_int, [c_int, c_int]),

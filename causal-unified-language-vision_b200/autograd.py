@@ -6,8 +6,8 @@
                  its autograd backward compute in five
                  launches forward+backward instead of ~25.
 
-Saved for backward: ``x`` (the caller's own tensor), ``u = xd A^T`` [M,r] and the dropout
-seed -- never a decoded weight, like bitsandbytes which saves only the packed bytes.
+Saved for backward: ``x`` (the caller's own tensor), ``u = drop(x) A^T`` [M,r] and the dropout
+seed (the mask is regenerated inside the kernels) -- never a decoded weight or a masked copy of x.
 """
 from __future__ import annotations
 
@@ -71,8 +71,7 @@ class QLoRALinear(torch.autograd.Function):
         b = B if B.dtype == torch.bfloat16 else B.to(torch.bfloat16)
         a = a.contiguous()
         b = b.contiguous()
-        xd = F.dropout_apply(x2, seed, p) if p > 0.0 else x2
-        u, us = F.lora_down(xd, a, scale)
+        u, us = F.lora_down(x2, a, scale, seed, p)   # dropout mask applied in shared memory
         y = F.qlora_fwd(x2, packed, qs, us, b)
         ctx.qs, ctx.lead, ctx.in_dtype = qs, lead, x.dtype
         ctx.scale, ctx.p, ctx.seed, ctx.grad_sink = float(scale), float(p), int(seed), grad_sink
@@ -88,24 +87,19 @@ class QLoRALinear(torch.autograd.Function):
         du = F.lora_bwd_du(dy2, b, ctx.scale)
         dx = None
         if need_x:
-            if ctx.p > 0.0:
-                dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, None, None)
-                dxl = F.gemm_bf16(du, a, True)
-                F.dropout_bwd_add_(dx, dxl, ctx.seed, ctx.p)
-            else:
-                dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, du, a)
+            dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, du, a, ctx.seed, ctx.p)
             dx = dx.reshape(*ctx.lead, -1).to(ctx.in_dtype)
         dA = dB = None
         if need_a or need_b:
-            xd = F.dropout_apply(x2, ctx.seed, ctx.p) if ctx.p > 0.0 else x2
             if ctx.grad_sink is not None:
                 sink = ctx.grad_sink
-                F.lora_grads(dy2, xd, u, du, ctx.scale, sink.dA, sink.dB, accumulate=sink.accumulate())
+                F.lora_grads(dy2, x2, u, du, ctx.scale, sink.dA, sink.dB, accumulate=sink.accumulate(),
+                             seed=ctx.seed, p=ctx.p)
                 sink.ready()  # may launch the bucket's all-reduce on the comm stream
             else:
                 dA = torch.empty_like(a)
                 dB = torch.empty_like(b)
-                F.lora_grads(dy2, xd, u, du, ctx.scale, dA, dB, accumulate=False)
+                F.lora_grads(dy2, x2, u, du, ctx.scale, dA, dB, accumulate=False, seed=ctx.seed, p=ctx.p)
                 dA = dA.to(ctx.param_dtypes[0]) if need_a else None
                 dB = dB.to(ctx.param_dtypes[1]) if need_b else None
         return dx, None, None, dA, dB, None, None, None, None

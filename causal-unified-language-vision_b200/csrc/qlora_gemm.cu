@@ -160,7 +160,10 @@ using DxV1 = GemmCfg<1, 2, 128, false, true, true, EPI_BF16, 4>;
 using DxV2 = GemmCfg<2, 1, 256, false, true, true, EPI_BF16, 4>;
 using DxV3 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4>;
 
-template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, 6>;   // u = xd A^T
+template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, 6>;   // u = x A^T
+template <int R> using DownDropCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, 6, 0, 0, true>;   // u = drop(x) A^T
+template <int R> using GradADropCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true>;
+using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 6>;           // masked du A (dropout backward)
 template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, 6>;      // du = s dy B
 template <int R> using GradACfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6>;  // dA^T tile, stored transposed
 template <int R> using GradBCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART, 6>;    // dB tile
@@ -228,26 +231,41 @@ extern "C" int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void*
     }
 }
 
-extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A, void* dx,
-                                int M, int N, int K, int r, cudaStream_t stream) {
+extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A,
+                                uint64_t seed, float drop_p, void* dx, int M, int N, int K, int r,
+                                cudaStream_t stream) {
     if (M == 0) return 0;
     if (!weight_ok(w) || dy == nullptr || dx == nullptr) return B2Q_ERR_ARG;
     const bool lora = du != nullptr && lora_A != nullptr && r > 0;
     if (M < 0 || N % 64 != 0 || K % 256 != 0 || (lora && r % 64 != 0)) return B2Q_ERR_SHAPE;
+    if (!(drop_p >= 0.f && drop_p < 1.f)) return B2Q_ERR_ARG;
+    const bool masked = lora && drop_p > 0.f;
+    int e = 0;
+    if (masked) {
+        // dx = mask * (du @ A) / (1 - p)  first (masked epilogue), then the decode GEMM accumulates onto it
+        GemmParams q;
+        memset(&q, 0, sizeof(q));
+        q.D = dx; q.ldd = K; q.alpha = 1.0f / (1.0f - drop_p); q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
+        q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.xf_ld = K;
+        if ((e = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return e;
+        if ((e = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return e;
+        if ((e = launch<GemmKNMask>(q, stream))) return e;
+    }
     int variant = g_variant_dx >= 0 ? g_variant_dx : env_int("B2Q_DX_VARIANT", 3);
     GemmParams p;
     memset(&p, 0, sizeof(p));
     fill_weight(p, w, K);
     p.D = dx; p.D2 = nullptr; p.ldd = K; p.alpha = 1.f; p.alpha2 = 0.f;
-    p.M = M; p.N = K; p.kb_main = N / 64; p.kb_tail = lora ? r / 64 : 0; p.splits = 1;
-    int e = 0;
+    p.accum_d = masked ? 1 : 0;
+    const bool tail = lora && !masked;
+    p.M = M; p.N = K; p.kb_main = N / 64; p.kb_tail = tail ? r / 64 : 0; p.splits = 1;
     auto setup = [&](int bnc, int group_m) -> int {
         p.group_m = group_m;
         if ((e = map_bf16_kmajor(&p.tmA, dy, M, N, 128))) return e;
         // packed W [N rows][K/2 bytes]: box (bnc/2 bytes) x 64 rows
         if ((e = make_map_2d(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->packed, K / 2, N, K / 2, bnc / 2, 64, false)))
             return e;
-        if (lora) {
+        if (tail) {
             if ((e = map_bf16_kmajor(&p.tmA2, du, M, r, 128))) return e;
             if ((e = map_bf16_mnmajor(&p.tmB2, lora_A, r, K))) return e;
         }
@@ -263,25 +281,29 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
 }
 
 template <int R>
-static int lora_down_r(const void* xd, const void* lora_A, float scale, void* u, void* us, int M, int K,
-                       cudaStream_t stream) {
+static int lora_down_r(const void* x, const void* lora_A, float scale, uint64_t seed, float drop_p, void* u, void* us,
+                       int M, int K, cudaStream_t stream) {
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.D = u; p.D2 = us; p.ldd = R; p.alpha = 1.f; p.alpha2 = scale;
+    const float keep_scale = 1.0f / (1.0f - drop_p);
+    p.D = u; p.D2 = us; p.ldd = R; p.alpha = keep_scale; p.alpha2 = scale * keep_scale;
     p.M = M; p.N = R; p.kb_main = K / 64; p.kb_tail = 0; p.splits = 1;
+    p.seed = seed; p.thresh16 = dropout_threshold(drop_p); p.xf_ld = K;
     int e;
-    if ((e = map_bf16_kmajor(&p.tmA, xd, M, K, 128))) return e;
+    if ((e = map_bf16_kmajor(&p.tmA, x, M, K, 128))) return e;
     if ((e = map_bf16_kmajor(&p.tmB, lora_A, R, K, R))) return e;
+    if (drop_p > 0.f) return launch<DownDropCfg<R>>(p, stream);
     return launch<DownCfg<R>>(p, stream);
 }
 
-extern "C" int b2q_lora_down(const void* xd, const void* lora_A, float scale, void* u, void* us, int M, int K, int r,
-                             cudaStream_t stream) {
+extern "C" int b2q_lora_down(const void* x, const void* lora_A, float scale, uint64_t seed, float drop_p, void* u,
+                             void* us, int M, int K, int r, cudaStream_t stream) {
     if (M == 0) return 0;
-    if (xd == nullptr || lora_A == nullptr || u == nullptr) return B2Q_ERR_ARG;
+    if (x == nullptr || lora_A == nullptr || u == nullptr) return B2Q_ERR_ARG;
     if (K % 64 != 0) return B2Q_ERR_SHAPE;
-    if (r == 64) return lora_down_r<64>(xd, lora_A, scale, u, us, M, K, stream);
-    if (r == 128) return lora_down_r<128>(xd, lora_A, scale, u, us, M, K, stream);
+    if (!(drop_p >= 0.f && drop_p < 1.f)) return B2Q_ERR_ARG;
+    if (r == 64) return lora_down_r<64>(x, lora_A, scale, seed, drop_p, u, us, M, K, stream);
+    if (r == 128) return lora_down_r<128>(x, lora_A, scale, seed, drop_p, u, us, M, K, stream);
     return B2Q_ERR_SHAPE;
 }
 
@@ -323,8 +345,9 @@ extern "C" size_t b2q_lora_grads_workspace_bytes(int M, int N, int K, int r) {
 }
 
 template <int R>
-static int lora_grads_r(const void* dy, const void* xd, const void* u, const void* du, float scale, void* dA, void* dB,
-                        int accumulate, float* ws, int M, int N, int K, cudaStream_t stream) {
+static int lora_grads_r(const void* dy, const void* xd, const void* u, const void* du, float scale, uint64_t seed,
+                        float drop_p, void* dA, void* dB, int accumulate, float* ws, int M, int N, int K,
+                        cudaStream_t stream) {
     const int kblocks = (M + 63) / 64;
     int e;
     // dA^T[k, j] = sum_m xd[m, k] * du[m, j]   (A = xd^T MN-major, B = du MN-major), stored transposed -> [r][K]
@@ -334,10 +357,14 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
         GemmParams p;
         memset(&p, 0, sizeof(p));
         p.D = wa; p.M = K; p.N = R; p.splits = sa; p.kb_main = (kblocks + sa - 1) / sa; p.kb_tail = 0;
+        p.seed = seed; p.thresh16 = dropout_threshold(drop_p); p.xf_ld = K;
         if ((e = map_bf16_mnmajor(&p.tmA, xd, M, K))) return e;
         if ((e = map_bf16_mnmajor(&p.tmB, du, M, R))) return e;
-        if ((e = launch<GradACfg<R>>(p, stream))) return e;
-        if ((e = b2q_reduce_partials(wa, sa, static_cast<int64_t>(R) * K, 1.0f, dA, accumulate, stream))) return e;
+        if (drop_p > 0.f) e = launch<GradADropCfg<R>>(p, stream); else e = launch<GradACfg<R>>(p, stream);
+        if (e) return e;
+        if ((e = b2q_reduce_partials(wa, sa, static_cast<int64_t>(R) * K, 1.0f / (1.0f - drop_p), dA, accumulate,
+                                     stream)))
+            return e;
     }
     // dB[n, j] = scale * sum_m dy[m, n] * u[m, j]
     const int sb = grad_splits(N / 128, kblocks);
@@ -354,17 +381,18 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
     return 0;
 }
 
-extern "C" int b2q_lora_grads(const void* dy, const void* xd, const void* u, const void* du, float scale, void* dA,
-                              void* dB, int accumulate, void* workspace, size_t workspace_bytes, int M, int N, int K,
-                              int r, cudaStream_t stream) {
+extern "C" int b2q_lora_grads(const void* dy, const void* xd, const void* u, const void* du, float scale,
+                              uint64_t seed, float drop_p, void* dA, void* dB, int accumulate, void* workspace,
+                              size_t workspace_bytes, int M, int N, int K, int r, cudaStream_t stream) {
+    if (!(drop_p >= 0.f && drop_p < 1.f)) return B2Q_ERR_ARG;
     if (dy == nullptr || xd == nullptr || u == nullptr || du == nullptr || dA == nullptr || dB == nullptr ||
         workspace == nullptr)
         return B2Q_ERR_ARG;
     if (K % 128 != 0 || N % 128 != 0 || M <= 0) return B2Q_ERR_SHAPE;
     if (workspace_bytes < b2q_lora_grads_workspace_bytes(M, N, K, r)) return B2Q_ERR_WORKSPACE;
     float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~static_cast<uintptr_t>(255));
-    if (r == 64) return lora_grads_r<64>(dy, xd, u, du, scale, dA, dB, accumulate, ws, M, N, K, stream);
-    if (r == 128) return lora_grads_r<128>(dy, xd, u, du, scale, dA, dB, accumulate, ws, M, N, K, stream);
+    if (r == 64) return lora_grads_r<64>(dy, xd, u, du, scale, seed, drop_p, dA, dB, accumulate, ws, M, N, K, stream);
+    if (r == 128) return lora_grads_r<128>(dy, xd, u, du, scale, seed, drop_p, dA, dB, accumulate, ws, M, N, K, stream);
     return B2Q_ERR_SHAPE;
 }
 

@@ -34,7 +34,8 @@ namespace b2q {
 enum EpiKind : int {
     EPI_BF16 = 0,      // D bf16 [M, ldd] = alpha * acc   (+ optional D2 = alpha2 * acc)
     EPI_F32_PART = 1,  // fp32 partial [split][M][N]
-    EPI_F32_PART_T = 2 // fp32 partial, transposed [split][N][M]
+    EPI_F32_PART_T = 2,// fp32 partial, transposed [split][N][M]
+    EPI_BF16_MASK = 3  // D bf16 [M, ldd] = keep(row*ldd+col) ? alpha * acc : 0   (LoRA-dropout backward)
 };
 
 struct GemmParams {
@@ -55,11 +56,19 @@ struct GemmParams {
     int kpr;           // absmax blocks per W row (= K_w / 64)          (B_DEC)
     int m_tiles, n_tiles;
     int group_m;       // rasterisation: m-tiles per L2 slab
+    int accum_d;       // EPI_BF16: D = bf16(D + alpha * acc)  (read-modify-write of the caller's buffer)
+    // LoRA dropout (A_XF transform / EPI_BF16_MASK): keep(i) for element i = row * xf_ld + col of the
+    // activation the mask belongs to (b2q_internal.h dropout_keep)
+    unsigned long long seed;
+    unsigned int thresh16;
+    long long xf_ld;
 };
 
 template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_, int NG_ = 2,
-          int PST_ = 6>
+          int PST_ = 6, bool A_XF_ = false>
 struct GemmCfg {
+    static constexpr bool A_XF = A_XF_;           // dropout mask applied to the A tile in shared memory
+    static constexpr int XF_THREADS = A_XF_ ? 256 : 0;
     static constexpr int NG = B_DEC_ ? NG_ : 0;   // decode groups (each BNC threads)
     static constexpr int PST = B_DEC_ ? PST_ : 0; // packed-NF4 ring depth
     static constexpr int CG = CG_;          // CTAs per MMA (cta_group)
@@ -85,7 +94,9 @@ struct GemmCfg {
                                      : TMEM_COLS_RAW <= 256 ? 256 : 512;
     static constexpr int NDT = B_DEC ? BNC : 0;         // decode threads per group
     static constexpr int NDW = NDT / 32;                // decode warps per group (arrivals per stage)
-    static constexpr int THREADS = 256 + NG * NDT;
+    static constexpr int THREADS = 256 + NG * NDT + XF_THREADS;
+    static_assert(!(A_XF_ && B_DEC_), "A transform and B decode share the warps 8+");
+    static_assert(!A_XF_ || (MT_ == 1 && CG_ == 1), "A transform: single 128-row tile, single CTA");
     static constexpr int BAR_BYTES = 1024;              // barriers + tmem ptr + code256
     static constexpr int CODE256_BYTES = B_DEC ? 1024 : 0;
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + BAR_BYTES + CODE256_BYTES;
@@ -128,7 +139,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a); };
     auto pk_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + s); };
     auto pk_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + PST + s); };
-    constexpr int NBARS = 2 * STAGES + 2 * ACC_STAGES + 2 * PST;
+    auto xf_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + 2 * PST + s); };
+    constexpr int NBARS = 2 * STAGES + 2 * ACC_STAGES + 2 * PST + (Cfg::A_XF ? STAGES : 0);
     static_assert(8 * NBARS + 8 <= Cfg::BAR_BYTES, "barrier area");
     const uint32_t tmem_slot = bar_base + 8u * NBARS;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + 8 * NBARS);
@@ -160,6 +172,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             mbar_init(full_bar(s), CG * (1 + Cfg::NDW));  // per CTA: producer (+tx) + one arrive per decode warp
             mbar_init(empty_bar(s), 1);                   // tcgen05.commit
         }
+        if constexpr (Cfg::A_XF)
+            for (int s = 0; s < STAGES; ++s) mbar_init(xf_bar(s), Cfg::XF_THREADS / 32);  // one arrive per transform warp
         for (int s = 0; s < PST; ++s) {
             mbar_init(pk_bar(s), 1);                      // packed-ring producer (+tx)
             mbar_init(pk_empty_bar(s), Cfg::NDW);         // decode warps, once the bytes are in registers
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 mbar_wait(tempty_bar(as), aph ^ 1u);
                 tc_fence_after();
                 for (int kb = 0; kb < kb_total; ++kb) {
-                    mbar_wait(full_bar(s), ph);
+                    mbar_wait(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph);
                     tc_fence_after();
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
@@ -319,17 +333,43 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     tmem_ld_wait();
                     const int col0 = n0 + c * 32;
                     if (row < p.M && col0 < p.N) {
-                        if constexpr (Cfg::EPI == EPI_BF16) {
+                        if constexpr (Cfg::EPI == EPI_BF16 || Cfg::EPI == EPI_BF16_MASK) {
                             uint32_t o[16];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                o[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.alpha,
-                                                   __uint_as_float(v[2 * j + 1]) * p.alpha);
                             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) +
                                                                   static_cast<long long>(row) * p.ldd + col0);
+                            if constexpr (Cfg::EPI == EPI_BF16_MASK) {
+                                const unsigned long long e0 = static_cast<unsigned long long>(row) * p.xf_ld + col0;
+                                const uint32_t j0 = static_cast<uint32_t>(e0 >> 1);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const uint32_t h = dropout_hash32(static_cast<uint32_t>(p.seed),
+                                                                      static_cast<uint32_t>(p.seed >> 32), j0 + j);
+                                    const float lo = (h & 0xFFFFu) >= p.thresh16 ? __uint_as_float(v[2 * j]) * p.alpha : 0.f;
+                                    const float hi = (h >> 16) >= p.thresh16 ? __uint_as_float(v[2 * j + 1]) * p.alpha : 0.f;
+                                    o[j] = pack_bf16x2(lo, hi);
+                                }
+                            } else if (p.accum_d) {
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    const uint4 old = dst[j4];
+                                    const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) {
+                                        const int j = 4 * j4 + jj;
+                                        const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&ow[jj]);
+                                        o[j] = pack_bf16x2(__bfloat162float(ob.x) + __uint_as_float(v[2 * j]) * p.alpha,
+                                                           __bfloat162float(ob.y) + __uint_as_float(v[2 * j + 1]) * p.alpha);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    o[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.alpha,
+                                                       __uint_as_float(v[2 * j + 1]) * p.alpha);
+                            }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                            if (p.D2 != nullptr) {
+                            if (Cfg::EPI == EPI_BF16 && p.D2 != nullptr) {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
                                     o[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * p.alpha2,
@@ -363,6 +403,56 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
         }
     } else if (warp >= 8) {
+      if constexpr (Cfg::A_XF) {
+        // ============================================ A-operand transform ====
+        // LoRA dropout: zero the dropped elements of the A tile in place (the 1/(1-p) scale is folded
+        // into the epilogue).  256 threads, four 16-byte chunks (8 bf16) each per stage; chunk q sits
+        // at byte q*16 of the stage: row q>>3, physical chunk q&7 holds logical chunk (q&7)^(row&7).
+        const int t = threadIdx.x - 256;
+        const uint32_t seed_lo = static_cast<uint32_t>(p.seed), seed_hi = static_cast<uint32_t>(p.seed >> 32);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            int mt_i, nt_i, split;
+            tile_coords(p, tile, mt_i, nt_i, split);
+            const int row0 = mt_i * Cfg::TILE_M;
+            const int kb0 = split * p.kb_main;
+            for (int kb = 0; kb < kb_total; ++kb) {
+                const int k0 = (kb0 + kb) * 64;
+                mbar_wait(full_bar(s), ph);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = t + 256 * i;
+                    const int rr = (q >> 3) & 63, cl = (q & 7) ^ (rr & 7);
+                    long long e0;
+                    if constexpr (!Cfg::A_MN) {   // rows = MN coordinate, 64 contraction elements per row
+                        const int row = q >> 3;
+                        e0 = static_cast<long long>(row0 + row) * p.xf_ld + k0 + ((q & 7) ^ (row & 7)) * 8;
+                    } else {                      // rows = contraction coordinate, two boxes of 64 MN elements
+                        e0 = static_cast<long long>(k0 + rr) * p.xf_ld + row0 + (q >> 9) * 64 + cl * 8;
+                    }
+                    const uint32_t j0 = static_cast<uint32_t>(static_cast<unsigned long long>(e0) >> 1);
+                    const uint32_t addr = a_stage(s) + q * 16;
+                    uint32_t w[4];
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t h = dropout_hash32(seed_lo, seed_hi, j0 + j);
+                        const uint32_t m = ((h & 0xFFFFu) >= p.thresh16 ? 0x0000FFFFu : 0u) |
+                                           ((h >> 16) >= p.thresh16 ? 0xFFFF0000u : 0u);
+                        w[j] &= m;
+                    }
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                                 "r"(w[3]) : "memory");
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xf_bar(s));
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+      }
       if constexpr (Cfg::B_DEC) {
         // ======================================================= NF4 decode ====
         // NG groups of BNC threads; group g takes ring positions it with it % NG == g.  One thread

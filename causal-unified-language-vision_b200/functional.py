@@ -249,16 +249,18 @@ def dropout_bwd_add_(dx: torch.Tensor, dxl: torch.Tensor, seed: int, p: float) -
 
 
 # --------------------------------------------------------------------------- QLoRA GEMMs ----
-def lora_down(xd: torch.Tensor, lora_A: torch.Tensor, scale: float):
-    """u = xd @ A^T, us = scale * u   (xd [M,K], A [r,K]) -> (u [M,r], us [M,r]) bf16."""
-    _need_cuda(xd, lora_A)
-    _need(xd, torch.bfloat16, "xd")
+def lora_down(x: torch.Tensor, lora_A: torch.Tensor, scale: float, seed: int = 0, p: float = 0.0):
+    """u = drop(x) @ A^T, us = scale * u   (x [M,K], A [r,K]) -> (u [M,r], us [M,r]) bf16.
+    The dropout mask keep(seed, i)/(1-p) is applied to the x tile in shared memory."""
+    _need_cuda(x, lora_A)
+    _need(x, torch.bfloat16, "x")
     _need(lora_A, torch.bfloat16, "lora_A")
-    M, K = xd.shape
+    M, K = x.shape
     r = lora_A.shape[0]
-    u = torch.empty((M, r), dtype=torch.bfloat16, device=xd.device)
-    us = torch.empty((M, r), dtype=torch.bfloat16, device=xd.device)
-    _lib.check(_lib.load().b2q_lora_down(_p(xd), _p(lora_A), scale, _p(u), _p(us), M, K, r, _stream()), "b2q_lora_down")
+    u = torch.empty((M, r), dtype=torch.bfloat16, device=x.device)
+    us = torch.empty((M, r), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().b2q_lora_down(_p(x), _p(lora_A), scale, seed, p, _p(u), _p(us), M, K, r, _stream()),
+               "b2q_lora_down")
     return u, us
 
 
@@ -296,8 +298,8 @@ def lora_bwd_du(dy: torch.Tensor, lora_B: torch.Tensor, scale: float) -> torch.T
 
 
 def qlora_bwd_dx(dy: torch.Tensor, packed: torch.Tensor, qs: QuantState, du: Optional[torch.Tensor],
-                 lora_A: Optional[torch.Tensor]) -> torch.Tensor:
-    """dx = dy @ dequant(W) (+ du @ A) in one tcgen05 kernel.  dy [M,N] bf16 -> dx [M,K] bf16."""
+                 lora_A: Optional[torch.Tensor], seed: int = 0, p: float = 0.0) -> torch.Tensor:
+    """dx = dy @ dequant(W) (+ keep * (du @ A) / (1-p)).  dy [M,N] bf16 -> dx [M,K] bf16."""
     _need_cuda(dy, packed, du, lora_A)
     _need(dy, torch.bfloat16, "dy")
     M, N = dy.shape
@@ -311,8 +313,8 @@ def qlora_bwd_dx(dy: torch.Tensor, packed: torch.Tensor, qs: QuantState, du: Opt
         r = lora_A.shape[0]
     dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
     w = qs.c_weight(packed)
-    _lib.check(_lib.load().b2q_qlora_bwd_dx(_p(dy), ct.byref(w), _p(du), _p(lora_A), _p(dx), M, N, K, r, _stream()),
-               "b2q_qlora_bwd_dx")
+    _lib.check(_lib.load().b2q_qlora_bwd_dx(_p(dy), ct.byref(w), _p(du), _p(lora_A), seed, p, _p(dx), M, N, K, r,
+                                            _stream()), "b2q_qlora_bwd_dx")
     return dx
 
 
@@ -328,19 +330,20 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
-def lora_grads(dy, xd, u, du, scale: float, dA: torch.Tensor, dB: torch.Tensor, accumulate: bool = False):
-    """dA[r,K] (+)= du^T @ xd ; dB[N,r] (+)= scale * dy^T @ u.  dA / dB are written in place
+def lora_grads(dy, x, u, du, scale: float, dA: torch.Tensor, dB: torch.Tensor, accumulate: bool = False,
+               seed: int = 0, p: float = 0.0):
+    """dA[r,K] (+)= du^T @ drop(x) ; dB[N,r] (+)= scale * dy^T @ u.  dA / dB are written in place
     (they may be views into a flat gradient bucket)."""
-    _need_cuda(dy, xd, u, du, dA, dB)
-    for t, nm in ((dy, "dy"), (xd, "xd"), (u, "u"), (du, "du"), (dA, "dA"), (dB, "dB")):
+    _need_cuda(dy, x, u, du, dA, dB)
+    for t, nm in ((dy, "dy"), (x, "x"), (u, "u"), (du, "du"), (dA, "dA"), (dB, "dB")):
         _need(t, torch.bfloat16, nm)
     M, N = dy.shape
-    K = xd.shape[1]
+    K = x.shape[1]
     r = u.shape[1]
     lib = _lib.load()
     nbytes = int(lib.b2q_lora_grads_workspace_bytes(M, N, K, r))
     ws = _workspace(nbytes, dy.device)
-    _lib.check(lib.b2q_lora_grads(_p(dy), _p(xd), _p(u), _p(du), scale, _p(dA), _p(dB), int(accumulate), _p(ws),
+    _lib.check(lib.b2q_lora_grads(_p(dy), _p(x), _p(u), _p(du), scale, seed, p, _p(dA), _p(dB), int(accumulate), _p(ws),
                                   ws.numel(), M, N, K, r, _stream()), "b2q_lora_grads")
     return dA, dB
 

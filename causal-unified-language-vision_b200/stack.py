@@ -107,11 +107,10 @@ class QLoRALinearStack(nn.Module):
             packed, qs, A, B, s = self._weights(mod)
             x = self.inputs[A.shape[1]]
             seed = base_seed + i
-            xd = F.dropout_apply(x, seed, p) if p > 0 else x
-            u, us = F.lora_down(xd, A, s)
+            u, us = F.lora_down(x, A, s, seed, p)
             y = F.qlora_fwd(x, packed, qs, us, B)
             saved.append((u, seed))
-            del y, us, xd
+            del y, us
         for i in range(len(self.mods) - 1, -1, -1):
             mod = self.mods[i]
             packed, qs, A, B, s = self._weights(mod)
@@ -119,20 +118,13 @@ class QLoRALinearStack(nn.Module):
             dy = self.grads_out[B.shape[0]]
             u, seed = saved[i]
             if recompute:  # gradient checkpointing re-runs the forward inside backward (load_cullavo.py:91-93)
-                xd = F.dropout_apply(x, seed, p) if p > 0 else x
-                u, us = F.lora_down(xd, A, s)
+                u, us = F.lora_down(x, A, s, seed, p)
                 y = F.qlora_fwd(x, packed, qs, us, B)
                 del y, us
             du = F.lora_bwd_du(dy, B, s)
-            if p > 0:
-                dx = F.qlora_bwd_dx(dy, packed, qs, None, None)
-                F.dropout_bwd_add_(dx, F.gemm_bf16(du, A, True), seed, p)
-                xd = F.dropout_apply(x, seed, p)
-            else:
-                dx = F.qlora_bwd_dx(dy, packed, qs, du, A)
-                xd = x
+            dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)
             sink = self.sync.sink_for(mod)
-            F.lora_grads(dy, xd, u, du, s, sink.dA, sink.dB, accumulate=sink.accumulate())
+            F.lora_grads(dy, x, u, du, s, sink.dA, sink.dB, accumulate=sink.accumulate(), seed=seed, p=p)
             sink.ready()
             del dx, du
         self.sync.finish()

@@ -100,10 +100,12 @@ int b2q_dropout_bwd_add(void* dx_bf16, const void* dxl_bf16, int64_t n, uint64_t
  * unless noted.  Contract: K % 64 == 0, N % 64 == 0, r in {16,32,64,128,256} and r % 16 == 0
  * for the LoRA operands (r % 64 == 0 for the fused tails), 16-byte aligned rows.           */
 
-/* u = xd @ lora_A^T  (fp32 accumulate -> bf16);  us = bf16(scale * u) when us != NULL.
+/* u = drop(x) @ lora_A^T  (fp32 accumulate -> bf16);  us = bf16(scale * u) when us != NULL.
+ * drop(x) = x * keep(seed, i) / (1 - drop_p), applied to the x tile in shared memory (no masked copy
+ * of x in HBM); drop_p = 0 -> no dropout.
  * Replaces `lora_A(dropout(x))` in peft.tuners.lora.bnb.Linear4bit.forward. */
-int b2q_lora_down(const void* xd, const void* lora_A, float scale, void* u, void* us, int M, int K, int r,
-                  cudaStream_t stream);
+int b2q_lora_down(const void* x, const void* lora_A, float scale, uint64_t seed, float drop_p, void* u, void* us,
+                  int M, int K, int r, cudaStream_t stream);
 
 /* y = x @ dequant(W)^T + us @ lora_B^T  in one kernel: packed NF4 staged by TMA, decoded in
  * registers, written to swizzled shared memory, consumed by tcgen05.mma with the accumulator in
@@ -118,20 +120,23 @@ int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void* us, const 
 int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, void* du, int M, int N, int r,
                     cudaStream_t stream);
 
-/* dx = dy @ dequant(W) + du @ lora_A  in one kernel (same decode, W consumed as an MN-major
- * operand, no transposed or bf16 copy of W).  du may be NULL (base only).
- * Replaces `MatMul4Bit.backward` (second dequantize_4bit + cuBLAS) plus the backward of
- * `lora_A` and the gradient add. */
-int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A, void* dx, int M,
-                     int N, int K, int r, cudaStream_t stream);
+/* dx = dy @ dequant(W) + keep * (du @ lora_A) / (1 - drop_p)   (same decode, W consumed as an MN-major
+ * operand, no transposed or bf16 copy of W).  du may be NULL (base only).  drop_p = 0: one kernel, the
+ * LoRA term runs as tail K-blocks.  drop_p > 0: a masked-epilogue GEMM writes the LoRA term to dx, the
+ * decode GEMM then accumulates onto it in its epilogue (two launches, no extra buffer).
+ * Replaces `MatMul4Bit.backward` (second dequantize_4bit + cuBLAS) plus the backward of `lora_A`,
+ * of the dropout and the gradient add. */
+int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A, uint64_t seed,
+                     float drop_p, void* dx, int M, int N, int K, int r, cudaStream_t stream);
 
-/* dA[r,K] (+)= du^T @ xd ;  dB[N,r] (+)= scale * dy^T @ u   (bf16 outputs, fp32 split-M partials
- * in `workspace`, reduced in a fixed order).  dA / dB may point into flat gradient buckets.
+/* dA[r,K] (+)= du^T @ drop(x) ;  dB[N,r] (+)= scale * dy^T @ u   (bf16 outputs, fp32 split-M partials
+ * in `workspace`, reduced in a fixed order; the dropout mask is regenerated in shared memory from
+ * (seed, drop_p)).  dA / dB may point into flat gradient buckets.
  * Replaces the weight-gradient halves of the autograd backward of `lora_A` / `lora_B`. */
 size_t b2q_lora_grads_workspace_bytes(int M, int N, int K, int r);
-int b2q_lora_grads(const void* dy, const void* xd, const void* u, const void* du, float scale, void* dA, void* dB,
-                   int accumulate, void* workspace, size_t workspace_bytes, int M, int N, int K, int r,
-                   cudaStream_t stream);
+int b2q_lora_grads(const void* dy, const void* x, const void* u, const void* du, float scale, uint64_t seed,
+                   float drop_p, void* dA, void* dB, int accumulate, void* workspace, size_t workspace_bytes, int M,
+                   int N, int K, int r, cudaStream_t stream);
 
 /* Generic bf16 GEMM on the same tcgen05 pipeline: d[M,N] = alpha * a[M,K] @ b[K,N] with b given
  * row-major [K,N] (b_is_kn = 1) or as [N,K] (b_is_kn = 0).  Used for du @ lora_A when dropout
