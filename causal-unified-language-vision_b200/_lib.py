@@ -61,6 +61,8 @@ SIGNATURES = {
     "b2q_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2q_reduce_partials": (c_int, [c_void_p, c_int, c_i64, c_float, c_void_p, c_int, c_void_p]),
     "b2q_set_variant": (c_int, [c_int, c_int]),
+    "b2q_debug_set_trace": (c_int, [c_void_p, c_int]),
+    "b2q_debug_set_prefetch": (c_int, [c_int]),
     "b2q_launch_count": (c_u64, []),
 }
 

@@ -113,8 +113,18 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* map, 
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// L2 prefetch of a 2D tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// D[tile] += smem tile, element-wise in the tensor map's data type (bf16), performed at the L2
+__device__ __forceinline__ void tma_reduce_add_2d(const void* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
                  "r"(src), "r"(c0), "r"(c1)
                  : "memory");
 }

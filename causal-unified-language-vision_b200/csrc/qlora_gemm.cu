@@ -83,6 +83,33 @@ static int map_bf16_mnmajor(CUtensorMap* m, const void* base, int kdim, int mn) 
                        true);
 }
 
+// bf16 output [rows][ld]: box 64 columns x 32 rows, 128-byte swizzle (TMA-store epilogue staging layout)
+static int map_bf16_out(CUtensorMap* m, const void* base, int rows, int cols, long long ld) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return B2Q_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * 2) & 15) != 0) return B2Q_ERR_ARG;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    auto encode = [&]() {
+        return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r = encode();
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        cudaFree(nullptr);
+        r = encode();
+    }
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled(D) -> CUresult %d (base %p, %d x %d, ld %lld)",
+                 static_cast<int>(r), base, rows, cols, ld);
+        return B2Q_ERR_DRIVER;
+    }
+    return 0;
+}
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -94,6 +121,10 @@ static int num_sms() {
     return n;
 }
 
+static long long* g_trace = nullptr;   // debug: phase trace buffer for the next launches (b2q_debug_set_trace)
+static int g_trace_tiles = 0;
+static int g_pf_dist = 0;
+
 template <class Cfg>
 static int launch(GemmParams& p, cudaStream_t stream) {
     static bool attr_set = false;
@@ -103,6 +134,9 @@ static int launch(GemmParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
+    p.trace = g_trace;
+    p.trace_tiles = g_trace_tiles;
+    p.pf_dist = g_pf_dist;
     p.m_tiles = (p.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
     p.n_tiles = (p.N + Cfg::BN - 1) / Cfg::BN;
     if (p.group_m <= 0) p.group_m = p.m_tiles;
@@ -159,11 +193,18 @@ using DxV0 = GemmCfg<1, 1, 128, false, true, true, EPI_BF16, 4>;
 using DxV1 = GemmCfg<1, 2, 128, false, true, true, EPI_BF16, 4>;
 using DxV2 = GemmCfg<2, 1, 256, false, true, true, EPI_BF16, 4>;
 using DxV3 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4>;
+// staged epilogues (packed ring 4 deep to make room for 16 KB of staging):
+// V4 = TMA store / reduce-add of 32 x 64 groups, V5 = warp-transposed, coalesced global stores (default)
+using FwdV4 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, 1>;
+using DxV4 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, 1>;
+using FwdV5 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, -1>;
+using DxV5 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, -1>;
 
 template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, 6>;   // u = x A^T
 template <int R> using DownDropCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, 6, 0, 0, true>;   // u = drop(x) A^T
 template <int R> using GradADropCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true>;
-using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 6>;           // masked du A (dropout backward)
+// dx += keep * (du A) / (1 - p): masked epilogue, TMA reduce-add into dx (dropout backward)
+using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 5, 0, 0, false, 1>;
 template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, 6>;      // du = s dy B
 template <int R> using GradACfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6>;  // dA^T tile, stored transposed
 template <int R> using GradBCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART, 6>;    // dB tile
@@ -191,6 +232,17 @@ extern "C" const char* b2q_error_string(int code) {
     }
 }
 
+extern "C" int b2q_debug_set_trace(void* buf, int tiles_per_cta) {
+    g_trace = static_cast<long long*>(buf);
+    g_trace_tiles = tiles_per_cta;
+    return 0;
+}
+
+extern "C" int b2q_debug_set_prefetch(int kblocks) {
+    g_pf_dist = kblocks;
+    return 0;
+}
+
 extern "C" int b2q_set_variant(int fwd_variant, int dx_variant) {
     g_variant_fwd = fwd_variant;
     g_variant_dx = dx_variant;
@@ -203,7 +255,7 @@ extern "C" int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void*
     if (!weight_ok(w) || x == nullptr || y == nullptr) return B2Q_ERR_ARG;
     const bool lora = us != nullptr && lora_B != nullptr && r > 0;
     if (M < 0 || K % 64 != 0 || N % 256 != 0 || (lora && r % 64 != 0)) return B2Q_ERR_SHAPE;
-    int variant = g_variant_fwd >= 0 ? g_variant_fwd : env_int("B2Q_FWD_VARIANT", 3);
+    int variant = g_variant_fwd >= 0 ? g_variant_fwd : env_int("B2Q_FWD_VARIANT", 5);
     GemmParams p;
     memset(&p, 0, sizeof(p));
     fill_weight(p, w, K);
@@ -227,8 +279,16 @@ extern "C" int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void*
         case 0: if ((e = setup(FwdV0::BNC, slab(FwdV0::TILE_M)))) return e; return launch<FwdV0>(p, stream);
         case 1: if ((e = setup(FwdV1::BNC, slab(FwdV1::TILE_M)))) return e; return launch<FwdV1>(p, stream);
         case 2: if ((e = setup(FwdV2::BNC, slab(FwdV2::TILE_M)))) return e; return launch<FwdV2>(p, stream);
-        default: if ((e = setup(FwdV3::BNC, slab(FwdV3::TILE_M)))) return e; return launch<FwdV3>(p, stream);
+        case 3: if ((e = setup(FwdV3::BNC, slab(FwdV3::TILE_M)))) return e; return launch<FwdV3>(p, stream);
+        default: break;
     }
+    if (variant == 4) {
+        if ((e = map_bf16_out(&p.tmD, y, M, N, N))) return e;
+        if ((e = setup(FwdV4::BNC, slab(FwdV4::TILE_M)))) return e;
+        return launch<FwdV4>(p, stream);
+    }
+    if ((e = setup(FwdV5::BNC, slab(FwdV5::TILE_M)))) return e;
+    return launch<FwdV5>(p, stream);
 }
 
 extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A,
@@ -241,22 +301,11 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
     if (!(drop_p >= 0.f && drop_p < 1.f)) return B2Q_ERR_ARG;
     const bool masked = lora && drop_p > 0.f;
     int e = 0;
-    if (masked) {
-        // dx = mask * (du @ A) / (1 - p)  first (masked epilogue), then the decode GEMM accumulates onto it
-        GemmParams q;
-        memset(&q, 0, sizeof(q));
-        q.D = dx; q.ldd = K; q.alpha = 1.0f / (1.0f - drop_p); q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
-        q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.xf_ld = K;
-        if ((e = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return e;
-        if ((e = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return e;
-        if ((e = launch<GemmKNMask>(q, stream))) return e;
-    }
-    int variant = g_variant_dx >= 0 ? g_variant_dx : env_int("B2Q_DX_VARIANT", 3);
+    int variant = g_variant_dx >= 0 ? g_variant_dx : env_int("B2Q_DX_VARIANT", 5);
     GemmParams p;
     memset(&p, 0, sizeof(p));
     fill_weight(p, w, K);
     p.D = dx; p.D2 = nullptr; p.ldd = K; p.alpha = 1.f; p.alpha2 = 0.f;
-    p.accum_d = masked ? 1 : 0;
     const bool tail = lora && !masked;
     p.M = M; p.N = K; p.kb_main = N / 64; p.kb_tail = tail ? r / 64 : 0; p.splits = 1;
     auto setup = [&](int bnc, int group_m) -> int {
@@ -273,11 +322,28 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
     };
     auto slab = [&](int tile_m) { int g = static_cast<int>((32ll << 20) / (2ll * N * tile_m)); return g < 1 ? 1 : g; };
     switch (variant) {
-        case 0: if ((e = setup(DxV0::BNC, slab(DxV0::TILE_M)))) return e; return launch<DxV0>(p, stream);
-        case 1: if ((e = setup(DxV1::BNC, slab(DxV1::TILE_M)))) return e; return launch<DxV1>(p, stream);
-        case 2: if ((e = setup(DxV2::BNC, slab(DxV2::TILE_M)))) return e; return launch<DxV2>(p, stream);
-        default: if ((e = setup(DxV3::BNC, slab(DxV3::TILE_M)))) return e; return launch<DxV3>(p, stream);
+        case 0: if ((e = setup(DxV0::BNC, slab(DxV0::TILE_M)))) return e; e = launch<DxV0>(p, stream); break;
+        case 1: if ((e = setup(DxV1::BNC, slab(DxV1::TILE_M)))) return e; e = launch<DxV1>(p, stream); break;
+        case 2: if ((e = setup(DxV2::BNC, slab(DxV2::TILE_M)))) return e; e = launch<DxV2>(p, stream); break;
+        case 3: if ((e = setup(DxV3::BNC, slab(DxV3::TILE_M)))) return e; e = launch<DxV3>(p, stream); break;
+        case 4:
+            if ((e = map_bf16_out(&p.tmD, dx, M, K, K))) return e;
+            if ((e = setup(DxV4::BNC, slab(DxV4::TILE_M)))) return e;
+            e = launch<DxV4>(p, stream);
+            break;
+        default: if ((e = setup(DxV5::BNC, slab(DxV5::TILE_M)))) return e; e = launch<DxV5>(p, stream); break;
     }
+    if (e || !masked) return e;
+    // LoRA dropout: dx += keep * (du @ A) / (1 - p) -- masked epilogue, reduce-added into dx by the copy engine
+    GemmParams q;
+    memset(&q, 0, sizeof(q));
+    q.D = dx; q.ldd = K; q.alpha = 1.0f / (1.0f - drop_p); q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
+    q.accum_d = 1;
+    q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.xf_ld = K;
+    if ((e = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return e;
+    if ((e = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return e;
+    if ((e = map_bf16_out(&q.tmD, dx, M, K, K))) return e;
+    return launch<GemmKNMask>(q, stream);
 }
 
 template <int R>

@@ -43,6 +43,7 @@ struct GemmParams {
     CUtensorMap tmA2;  // tail A operand (bf16)
     CUtensorMap tmB;   // main B operand: bf16, or packed NF4 bytes when B_DEC
     CUtensorMap tmB2;  // tail B operand (bf16)
+    CUtensorMap tmD;   // EPI_TMA: D as a bf16 tensor [M][ldd], box 64 cols x 32 rows, SWIZZLE_128B (store / reduce-add)
     AbsmaxSrc am;
     const float* code16;
     void* D;
@@ -62,11 +63,25 @@ struct GemmParams {
     unsigned long long seed;
     unsigned int thresh16;
     long long xf_ld;
+    // optional phase trace (debug / profiling): clock64 stamps, [cta][tile][8]; nullptr = off
+    long long* trace;
+    int trace_tiles;
+    int pf_dist;       // L2 prefetch distance of the A operand in k-blocks (0 = off)
 };
 
 template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_, int NG_ = 2,
-          int PST_ = 6, bool A_XF_ = false>
+          int PST_ = 6, bool A_XF_ = false, int STG_ = 0>
 struct GemmCfg {
+    // STG > 0: the bf16 epilogue goes TMEM -> registers -> swizzled shared-memory staging (32 rows x 64
+    // columns per epilogue warp) -> TMA store (or TMA reduce-add when accum_d), so global memory sees whole
+    // 128-byte row segments written by the copy engine instead of 32 scattered 16-byte stores per warp
+    // instruction.
+    // STG < 0: same staging idea without the copy engine: each epilogue warp transposes 32 rows x 64 columns
+    // through a 4 KB swizzled tile and writes global memory itself, 4 whole 128-byte row segments per store
+    // instruction (or read-modify-write when accum_d).
+    static constexpr bool EPI_TMA = STG_ > 0;
+    static constexpr bool EPI_COAL = STG_ < 0;
+    static constexpr int STG_BYTES = STG_ != 0 ? 4 * 4096 : 0;
     static constexpr bool A_XF = A_XF_;           // dropout mask applied to the A tile in shared memory
     static constexpr int XF_THREADS = A_XF_ ? 256 : 0;
     static constexpr int NG = B_DEC_ ? NG_ : 0;   // decode groups (each BNC threads)
@@ -99,7 +114,9 @@ struct GemmCfg {
     static_assert(!A_XF_ || (MT_ == 1 && CG_ == 1), "A transform: single 128-row tile, single CTA");
     static constexpr int BAR_BYTES = 1024;              // barriers + tmem ptr + code256
     static constexpr int CODE256_BYTES = B_DEC ? 1024 : 0;
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + BAR_BYTES + CODE256_BYTES;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + BAR_BYTES + CODE256_BYTES + STG_BYTES;
+    static_assert(STG_ == 0 || EPI_ == EPI_BF16 || EPI_ == EPI_BF16_MASK, "staged epilogues: bf16 output only");
+    static_assert(STG_ == 0 || BN_ % 64 == 0, "staged epilogues work on 64-column groups");
 
     static_assert(BN % (16 * CG) == 0 && BN <= 256, "UMMA N");
     static_assert(ACC_COLS <= 512, "TMEM columns");
@@ -136,11 +153,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a); };
-    auto pk_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + s); };
-    auto pk_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + PST + s); };
-    auto xf_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES + 2 * PST + s); };
-    constexpr int NBARS = 2 * STAGES + 2 * ACC_STAGES + 2 * PST + (Cfg::A_XF ? STAGES : 0);
+    // one "accumulator drained" barrier per (accumulator stage, 128-row sub-tile): the next tile's MMAs into
+    // sub-tile 0 start while the epilogue is still draining sub-tile 1
+    auto tempty_bar = [&](int a, int mt) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a * MT + mt); };
+    constexpr int NB0 = 2 * STAGES + ACC_STAGES + ACC_STAGES * MT;
+    auto pk_bar = [&](int s) { return bar_base + 8u * (NB0 + s); };
+    auto pk_empty_bar = [&](int s) { return bar_base + 8u * (NB0 + PST + s); };
+    auto xf_bar = [&](int s) { return bar_base + 8u * (NB0 + 2 * PST + s); };
+    constexpr int NBARS = NB0 + 2 * PST + (Cfg::A_XF ? STAGES : 0);
     static_assert(8 * NBARS + 8 <= Cfg::BAR_BYTES, "barrier area");
     const uint32_t tmem_slot = bar_base + 8u * NBARS;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + 8 * NBARS);
@@ -166,6 +186,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             tma_prefetch_desc(&p.tmA2);
             tma_prefetch_desc(&p.tmB2);
         }
+        if constexpr (Cfg::EPI_TMA) tma_prefetch_desc(&p.tmD);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -180,7 +201,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
             mbar_init(tfull_bar(a), 1);                   // tcgen05.commit
-            mbar_init(tempty_bar(a), CG * 4);             // one arrive per epilogue warp, both CTAs
+            for (int mt = 0; mt < MT; ++mt) mbar_init(tempty_bar(a, mt), CG * 4);  // one arrive per epilogue warp, both CTAs
         }
         fence_mbar_init();
     }
@@ -199,7 +220,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
 
     // barrier addresses as seen for an arrive: the leader's copy when working as a pair
     auto full_bar_arrive = [&](int s) { return CG == 2 ? mapa(full_bar(s), 0) : full_bar(s); };
-    auto tempty_bar_arrive = [&](int a) { return CG == 2 ? mapa(tempty_bar(a), 0) : tempty_bar(a); };
+    auto tempty_bar_arrive = [&](int a, int mt) { return CG == 2 ? mapa(tempty_bar(a, mt), 0) : tempty_bar(a, mt); };
 
     if (warp == 0) {
         // ===================================================== TMA producer ====
@@ -235,6 +256,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                             load(dst + 8192, mapA, row0 + 64, k0);
                         }
                     }
+                    if constexpr (!Cfg::A_MN) {
+                        // pull the A tile of k-block kb + pf_dist into L2 now, so that its TMA load is an L2 hit
+                        if (p.pf_dist > 0 && !tail && kb + p.pf_dist < p.kb_main) {
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt)
+                                tma_prefetch_2d(mapA, k0 + p.pf_dist * 64,
+                                                m0 + (CG == 2 ? mt * 256 + static_cast<int>(rank) * 128 : mt * 128));
+                        }
+                    }
                     const int brow0 = n0 + static_cast<int>(rank) * BNC;
                     if (b_by_tma) {
                         const CUtensorMap* mapB = tail ? &p.tmB2 : &p.tmB;
@@ -262,14 +292,28 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
-            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-                mbar_wait(tempty_bar(as), aph ^ 1u);
-                tc_fence_after();
+            int tseq = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tseq) {
+                long long* tr = (p.trace != nullptr && tseq < p.trace_tiles)
+                                    ? p.trace + (static_cast<long long>(blockIdx.x) * p.trace_tiles + tseq) * 8 : nullptr;
+                long long full_wait = 0;
                 for (int kb = 0; kb < kb_total; ++kb) {
+                    long long w0 = 0;
+                    if (tr != nullptr) {
+                        w0 = clock64();
+                        if (kb == 0) tr[0] = w0;
+                    }
                     mbar_wait(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph);
                     tc_fence_after();
+                    if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
+                        if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
+                            if (tr != nullptr && mt == 0) tr[1] = clock64();
+                            mbar_wait(tempty_bar(as, mt), aph ^ 1u);
+                            tc_fence_after();
+                            if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
+                        }
                         const uint32_t d_tmem = tmem_base + as * ACC_COLS + mt * BN;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -282,7 +326,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         }
                     }
                     umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
-                    if (kb == kb_total - 1) umma_commit<CG>(tfull_bar(as));
+                    if (kb == kb_total - 1) {
+                        umma_commit<CG>(tfull_bar(as));
+                        if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
                 if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
@@ -315,13 +362,136 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         const int wq = warp & 3;  // TMEM lane quadrant this warp may access
         int as = 0;
         uint32_t aph = 0;
-        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        [[maybe_unused]] const uint32_t stg_base = smem_base + Cfg::RING_BYTES + Cfg::BAR_BYTES + Cfg::CODE256_BYTES;
+        int tseq = 0;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tseq) {
             int mt_i, nt_i, split;
             tile_coords(p, tile, mt_i, nt_i, split);
             const int m0 = mt_i * Cfg::TILE_M;
             const int n0 = nt_i * BN;
+            long long* tr = (p.trace != nullptr && tseq < p.trace_tiles && wq == 0 && lane == 0)
+                                ? p.trace + (static_cast<long long>(blockIdx.x) * p.trace_tiles + tseq) * 8 : nullptr;
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
+            if (tr != nullptr) tr[5] = clock64();
+            if constexpr (Cfg::EPI_COAL || Cfg::EPI_TMA) {
+                // group q = (mt, c): 32 TMEM lanes (rows) x 64 columns -> bf16 -> swizzled 32 x 128 B staging tile of this
+                // warp (row-per-lane writes), then either the copy engine stores / reduce-adds the tile (EPI_TMA) or the
+                // warp reads it back 4 rows x 128 B per instruction and writes global memory itself (EPI_COAL).
+                constexpr int GPM = BN / 64, NG64 = MT * GPM;
+                const uint32_t t_warp = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * ACC_COLS;
+                const uint32_t stg = stg_base + wq * 4096;
+                const float alpha_r = p.alpha;
+                const bool unit = alpha_r == 1.0f;
+                __nv_bfloat16* Dp = reinterpret_cast<__nv_bfloat16*>(p.D);
+                const long long ldd_r = p.ldd;
+                const int M_r = p.M;
+                const bool accum_r = p.accum_d != 0;
+#pragma unroll 1
+                for (int q = 0; q < NG64; ++q) {
+                    const int mt = q / GPM, c = q % GPM;
+                    const int row_t = m0 + (CG == 2 ? mt * 256 + static_cast<int>(rank) * 128 : mt * 128) + wq * 32;
+                    uint32_t o[32];
+                    {
+                        uint32_t v[32], w[32];
+                        tmem_ld_32x32(t_warp + q * 64, v);
+                        tmem_ld_32x32(t_warp + q * 64 + 32, w);
+                        tmem_ld_wait();
+                        if (unit) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                                o[16 + j] = pack_bf16x2(__uint_as_float(w[2 * j]), __uint_as_float(w[2 * j + 1]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                o[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * alpha_r, __uint_as_float(v[2 * j + 1]) * alpha_r);
+                                o[16 + j] = pack_bf16x2(__uint_as_float(w[2 * j]) * alpha_r, __uint_as_float(w[2 * j + 1]) * alpha_r);
+                            }
+                        }
+                    }
+                    if constexpr (Cfg::EPI == EPI_BF16_MASK) {
+                        // LoRA-dropout backward: zero the dropped elements (element index = row * xf_ld + col)
+                        const unsigned long long e0 = static_cast<unsigned long long>(row_t + lane) * p.xf_ld + (n0 + c * 64);
+                        const uint32_t j0 = static_cast<uint32_t>(e0 >> 1);
+                        const uint32_t s_lo = static_cast<uint32_t>(p.seed), s_hi = static_cast<uint32_t>(p.seed >> 32);
+                        const uint32_t thr = p.thresh16;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const uint32_t h = dropout_hash32(s_lo, s_hi, j0 + j);
+                            o[j] &= ((h & 0xFFFFu) >= thr ? 0x0000FFFFu : 0u) | ((h >> 16) >= thr ? 0xFFFF0000u : 0u);
+                        }
+                    }
+                    if (c == GPM - 1) {   // sub-tile mt drained: its last TMEM load has completed
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar_arrive(as, mt)); else mbar_arrive(tempty_bar(as, mt));
+                        }
+                    }
+                    if constexpr (Cfg::EPI_TMA) {
+                        if (lane == 0) tma_store_wait_read<0>();   // the copy engine has read the previous group
+                    }
+                    __syncwarp();   // (EPI_COAL) the previous group's read-back of the staging tile is complete
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * 128 + ((static_cast<uint32_t>(j ^ (lane & 7))) << 4)),
+                                     "r"(o[4 * j]), "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3]) : "memory");
+                    if constexpr (Cfg::EPI_TMA) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (row_t < M_r) {
+                                if (accum_r) tma_reduce_add_2d(&p.tmD, stg, n0 + c * 64, row_t);
+                                else tma_store_2d(&p.tmD, stg, n0 + c * 64, row_t);
+                            }
+                            tma_store_commit();
+                        }
+                    } else {
+                        __syncwarp();
+                        const int row_w = row_t + (lane >> 3);
+                        const int ch = lane & 7;
+                        uint4 val[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {   // rows i*4 + lane/8
+                            const int r = i * 4 + (lane >> 3);
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(val[i].x), "=r"(val[i].y), "=r"(val[i].z), "=r"(val[i].w)
+                                         : "r"(stg + r * 128 + ((static_cast<uint32_t>(ch ^ (r & 7))) << 4)));
+                        }
+                        __nv_bfloat16* gp = Dp + static_cast<long long>(row_w) * ldd_r + (n0 + c * 64 + ch * 8);
+                        if (accum_r) {
+                            uint4 old[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                old[i] = make_uint4(0u, 0u, 0u, 0u);
+                                if (row_w + i * 4 < M_r) old[i] = *reinterpret_cast<const uint4*>(gp + static_cast<long long>(i) * 4 * ldd_r);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t a[4] = {old[i].x, old[i].y, old[i].z, old[i].w};
+                                uint32_t b[4] = {val[i].x, val[i].y, val[i].z, val[i].w};
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&a[t]);
+                                    const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&b[t]);
+                                    b[t] = pack_bf16x2(__bfloat162float(x2.x) + __bfloat162float(y2.x),
+                                                       __bfloat162float(x2.y) + __bfloat162float(y2.y));
+                                }
+                                val[i] = make_uint4(b[0], b[1], b[2], b[3]);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t ok = (row_w + i * 4 < M_r) ? 1u : 0u;
+                            asm volatile("{\n\t.reg .pred P1;\n\tsetp.ne.b32 P1, %5, 0;\n\t@P1 st.global.v4.b32 [%0], {%1,%2,%3,%4};\n\t}\n"
+                                         ::"l"(gp + static_cast<long long>(i) * 4 * ldd_r), "r"(val[i].x), "r"(val[i].y),
+                                           "r"(val[i].z), "r"(val[i].w), "r"(ok) : "memory");
+                        }
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
                 const int row = m0 + (CG == 2 ? mt * 256 + static_cast<int>(rank) * 128 : mt * 128) + wq * 32 + lane;
@@ -394,13 +564,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         }
                     }
                 }
+                tc_fence_before();   // sub-tile mt drained
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar_arrive(as, mt)); else mbar_arrive(tempty_bar(as, mt));
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar_arrive(as)); else mbar_arrive(tempty_bar(as));
-            }
+            if (tr != nullptr) tr[6] = clock64();
             if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+        }
+        if constexpr (Cfg::EPI_TMA) {
+            if (lane == 0) tma_store_wait<0>();   // all bulk stores of this warp are complete before the CTA exits
         }
     } else if (warp >= 8) {
       if constexpr (Cfg::A_XF) {

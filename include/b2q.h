@@ -122,8 +122,8 @@ int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, void* du, i
 
 /* dx = dy @ dequant(W) + keep * (du @ lora_A) / (1 - drop_p)   (same decode, W consumed as an MN-major
  * operand, no transposed or bf16 copy of W).  du may be NULL (base only).  drop_p = 0: one kernel, the
- * LoRA term runs as tail K-blocks.  drop_p > 0: a masked-epilogue GEMM writes the LoRA term to dx, the
- * decode GEMM then accumulates onto it in its epilogue (two launches, no extra buffer).
+ * LoRA term runs as tail K-blocks.  drop_p > 0: the decode GEMM writes dy @ dequant(W) to dx, then a
+ * masked-epilogue GEMM reduce-adds the LoRA term into dx (two launches, no extra buffer).
  * Replaces `MatMul4Bit.backward` (second dequantize_4bit + cuBLAS) plus the backward of `lora_A`,
  * of the dropout and the gradient add. */
 int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A, uint64_t seed,
@@ -149,8 +149,18 @@ int b2q_reduce_partials(const float* partial, int splits, int64_t n, float scale
                         cudaStream_t stream);
 
 /* Tuning hook: tile configuration of the two main kernels (0: 1 CTA, 128x128; 1: 1 CTA, 256x128;
- * 2: CTA pair, 256x256; 3: CTA pair, 512x256 [default]); -1 keeps the default / B2Q_*_VARIANT env. */
+ * 2: CTA pair, 256x256; 3: CTA pair, 512x256, direct epilogue stores; 4: as 3 with a TMA-store epilogue;
+ * 5: as 3 with a warp-transposed, coalesced-store epilogue [default]); -1 keeps the default / B2Q_*_VARIANT env. */
 int b2q_set_variant(int fwd_variant, int dx_variant);
+
+/* Debug / profiling: when buf != NULL every following tcgen05 GEMM launch records clock64 stamps of its
+ * pipeline phases for the first `tiles_per_cta` tiles of every CTA into buf[cta][tile][8] (int64):
+ * 0 MMA warp reaches the tile, 1 first operand stage ready, 2/3 accumulator sub-tile 0/1 free, 4 last MMA
+ * committed, 5 epilogue sees the accumulator, 6 epilogue done.  NULL switches it off (default). */
+int b2q_debug_set_trace(void* buf, int tiles_per_cta);
+
+/* Tuning: L2 prefetch distance (in 64-wide k-blocks) of the activation operand in the tcgen05 GEMMs; 0 = off. */
+int b2q_debug_set_prefetch(int kblocks);
 
 /* Launch counter (every kernel this library launches increments it); for bench.py's gpu_launches. */
 uint64_t b2q_launch_count(void);

@@ -90,6 +90,10 @@ def main():
                 med, best = timeit(lambda: F.qlora_bwd_dx(dy, packed, qs, du if lora else None, A if lora else None))
                 emit(kernel="qlora_bwd_dx", variant=v, lora=lora, N=N, K=K, M=M, ms=med, best_ms=best,
                      tflops=fl / med / 1e9)
+                if lora:  # LoRA dropout p = 0.05 (the training configuration)
+                    med, best = timeit(lambda: F.qlora_bwd_dx(dy, packed, qs, du, A, 1234, 0.05))
+                    emit(kernel="qlora_bwd_dx_drop", variant=v, lora=lora, N=N, K=K, M=M, ms=med, best_ms=best,
+                         tflops=fl / med / 1e9)
         del x, dy, Wb, packed
         torch.cuda.empty_cache()
 

@@ -114,7 +114,7 @@ CASES = [  # M, N, K, r, double_quant
 
 
 @pytest.mark.parametrize("M,N,K,r,dq", CASES)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_linear_fwd_bwd_against_oracle(F, cuda_dev, M, N, K, r, dq, variant):
     from oracle.qlora import make_case, qlora_linear_fwd_bwd, rel_err
 
