@@ -168,6 +168,15 @@ class GradSync:
         self._done_events = []
 
     # ---- helpers ------------------------------------------------------------------------
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Make every rank start from rank ``src``'s LoRA weights (what DDP does at construction;
+        /root/reference/trainer/utils_trainer.py:35-36 relies on it through ``accel.prepare``)."""
+        if self.world <= 1:
+            return
+        for m in self.modules:
+            for which in ("lora_A", "lora_B"):
+                dist.broadcast(getattr(m, which)[self.adapter].weight.data, src=src, group=self.group)
+
     def zero_grad(self) -> None:
         for b in self.buckets:
             b.flat.zero_()

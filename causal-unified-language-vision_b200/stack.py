@@ -74,6 +74,7 @@ class QLoRALinearStack(nn.Module):
                 prm.data = prm.data.to(torch.bfloat16)
         self.mods: List[LoraLinear4bit] = [layer[name] for layer in self.layers for name, _, _ in self.shapes]
         self.sync = GradSync(self.mods, adapter, process_group=process_group, bucket_bytes=bucket_bytes)
+        self.sync.broadcast_parameters(0)  # LoRA init draws from the global RNGs: replicas start from rank 0's copy
         # fixed synthetic activations per distinct width (rank-dependent seed for the activations)
         self.inputs = {}
         self.grads_out = {}

@@ -58,6 +58,12 @@ def _worker(rank, world, port, q):
     par = importlib.import_module("causal-unified-language-vision_b200.parallel")
     mods = _mods()
     gs = par.GradSync(mods, "a", bucket_bytes=3000, grad_dtype=torch.float32)
+    # replicas that start from different weights are made identical by the parameter broadcast
+    with torch.no_grad():
+        for m in mods:
+            m.lora_A["a"].weight.add_(float(rank))
+    gs.broadcast_parameters(0)
+    w0 = float(mods[0].lora_A["a"].weight.sum())
     gs.begin_step()
     for i, m in enumerate(reversed(mods)):  # backward order
         s = gs.sink_for(m)
@@ -66,7 +72,7 @@ def _worker(rank, world, port, q):
         s.ready()
     gs.finish()
     out = [(float(m.lora_A["a"].weight.grad.mean()), float(m.lora_B["a"].weight.grad.mean())) for m in reversed(mods)]
-    q.put((rank, out))
+    q.put((rank, (out, w0)))
     dist.destroy_process_group()
 
 
@@ -83,6 +89,7 @@ def test_two_rank_allreduce_mean_gloo():
         p.join(timeout=30)
         assert p.exitcode == 0
     # mean over ranks of (rank+1)*c = 1.5*c
+    assert res[0][1] == res[1][1]  # broadcast_parameters: both ranks hold rank 0's weights
     for r in (0, 1):
-        for i, (a, b) in enumerate(res[r]):
+        for i, (a, b) in enumerate(res[r][0]):
             assert abs(a - 1.5 * (i + 1)) < 1e-6 and abs(b - 15.0 * (i + 1)) < 1e-6
