@@ -266,3 +266,98 @@ def test_grad_sync_buckets_single_rank(F, cuda_dev):
     mod(x).backward(st.grads_out[mod.out_features])
     after = mod.lora_A["step1"].weight.grad
     assert float((after.float() - 2 * before.float()).abs().max()) <= 2e-2 * float(before.float().abs().max()) + 1e-6
+
+
+REAL_SHAPES = [  # N, K, r  -- projections of the model families the reference loads
+    (1024, 4096, 64),    # Mistral GQA k/v projection
+    (11008, 4096, 64),   # LLaMA-2 / Vicuna gate/up (LLaVA-1.5, the reference's default checkpoint)
+    (4096, 11008, 128),  # LLaMA down projection at r = 128 (BASELINE config C5's rank)
+    (1024, 1024, 64),    # CLIP ViT-L attention projection
+]
+
+
+@pytest.mark.parametrize("N,K,r", REAL_SHAPES)
+def test_real_projection_shapes_against_oracle(F, cuda_dev, N, K, r):
+    from oracle.qlora import make_case, qlora_linear_fwd_bwd, rel_err
+
+    M = 577  # one CLIP-L/14-336 image worth of rows incl. CLS: ragged against every tile size
+    case = make_case(M, N, K, r, seed=N + K, double_quant=True)
+    s = 16.0 / r
+    ref = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], s, case["dy"], mode="bf16")
+    packed, qs = _state_to_gpu(case["state"], cuda_dev)
+    x, dy, A, B = (case[k].to(cuda_dev) for k in ("x", "dy", "A", "B"))
+    u, us = F.lora_down(x, A, s)
+    y = F.qlora_fwd(x, packed, qs, us, B)
+    du = F.lora_bwd_du(dy, B, s)
+    dx = F.qlora_bwd_dx(dy, packed, qs, du, A)
+    dA = torch.zeros_like(A)
+    dB = torch.zeros_like(B)
+    F.lora_grads(dy, x, u, du, s, dA, dB)
+    torch.cuda.synchronize()
+    for name, got in (("y", y), ("dx", dx), ("dA", dA), ("dB", dB)):
+        assert rel_err(got.cpu(), ref[name]) <= TOL, (name, rel_err(got.cpu(), ref[name]))
+
+
+def test_empty_fp32_and_strided_inputs(F, cuda_dev):
+    """Edge cases of the module surface: zero rows, fp32 activations (cast in, cast back), non-contiguous rows."""
+    lora = importlib.import_module("causal-unified-language-vision_b200.lora")
+    stackmod = importlib.import_module("causal-unified-language-vision_b200.stack")
+    gen = torch.Generator(device=cuda_dev).manual_seed(0)
+    lin = stackmod.make_quantized_linear(512, 256, cuda_dev, gen)
+    mod = lora.LoraLinear4bit(lin, "step1", r=64, lora_alpha=16, lora_dropout=0.0).to(cuda_dev)
+    for p in mod.parameters():
+        if p.dtype == torch.float32:
+            p.data = p.data.to(torch.bfloat16)
+    with torch.no_grad():
+        mod.lora_B["step1"].weight.normal_(0, 0.02)
+    # zero rows
+    y0 = mod(torch.empty(0, 256, device=cuda_dev, dtype=torch.bfloat16))
+    assert y0.shape == (0, 512)
+    # fp32 in -> fp32 out, same values as the bf16 call on the rounded input
+    x32 = torch.randn(3, 50, 256, device=cuda_dev)
+    y32 = mod(x32)
+    assert y32.dtype == torch.float32 and y32.shape == (3, 50, 512)
+    assert torch.equal(y32, mod(x32.bfloat16()).float())
+    # non-contiguous rows (a slice of a wider tensor) give the same result as the packed copy
+    wide = torch.randn(64, 512, device=cuda_dev, dtype=torch.bfloat16)
+    xs = wide[:, 128:384]
+    assert not xs.is_contiguous()
+    assert torch.equal(mod(xs), mod(xs.contiguous()))
+    # shapes outside the kernel contract fail loudly instead of silently falling back
+    bad = stackmod.make_quantized_linear(192, 256, cuda_dev, gen)   # N % 256 != 0
+    with pytest.raises(RuntimeError):
+        bad(torch.randn(4, 256, device=cuda_dev, dtype=torch.bfloat16))
+
+
+def test_checkpoint_recompute_reproduces_dropout_mask(F, cuda_dev):
+    """Non-reentrant gradient checkpointing (load_cullavo.py:91-93) re-runs forward inside backward; the dropout seed
+    comes from torch's CPU generator, which checkpoint restores, so gradients equal the un-checkpointed run."""
+    from torch.utils.checkpoint import checkpoint
+
+    lora = importlib.import_module("causal-unified-language-vision_b200.lora")
+    stackmod = importlib.import_module("causal-unified-language-vision_b200.stack")
+    gen = torch.Generator(device=cuda_dev).manual_seed(1)
+    lin = stackmod.make_quantized_linear(256, 256, cuda_dev, gen)
+    mod = lora.LoraLinear4bit(lin, "step1", r=64, lora_alpha=16, lora_dropout=0.05).to(cuda_dev)
+    for p in mod.parameters():
+        if p.dtype == torch.float32:
+            p.data = p.data.to(torch.bfloat16)
+    with torch.no_grad():
+        mod.lora_B["step1"].weight.normal_(0, 0.02)
+    mod.train()
+    x = torch.randn(300, 256, device=cuda_dev, dtype=torch.bfloat16)
+    dy = torch.randn(300, 256, device=cuda_dev, dtype=torch.bfloat16)
+
+    def run(use_ckpt):
+        torch.manual_seed(123)
+        for p in mod.parameters():
+            p.grad = None
+        xi = x.clone().requires_grad_(True)
+        y = checkpoint(mod, xi, use_reentrant=False) if use_ckpt else mod(xi)
+        y.backward(dy)
+        return y.detach(), xi.grad, mod.lora_A["step1"].weight.grad.clone(), mod.lora_B["step1"].weight.grad.clone()
+
+    a = run(False)
+    b = run(True)
+    for t0, t1 in zip(a, b):
+        assert torch.equal(t0, t1)
