@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--recompute", action="store_true", help="also re-run the forward inside backward (grad ckpt)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-opt", action="store_true", help="skip the (reported-only) fused optimizer timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -298,6 +299,27 @@ def main():
         e2e = {"value": M * world / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ems, "api": "LoraLinear4bit.forward + autograd (QLoRALinear) -> C ABI"}
 
+    # ---- the step either side of the path: fused clip + AdamW on the flat buckets (reported, not part of `value`) ---
+    opt_info = None
+    if not args.no_opt:
+        optim = import_module("causal-unified-language-vision_b200.optim")
+        opt = optim.FusedLoraAdamW(stack.sync, lr=2e-5, weight_decay=0.0)
+        for _ in range(2):
+            opt.clip_grad_norm_(10.0)
+            opt.step()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(5):
+            opt.clip_grad_norm_(10.0)
+            opt.step()
+        o1.record()
+        barrier()
+        oms = o0.elapsed_time(o1) / 5
+        nel = sum(f.numel() for f in opt.pflat)
+        opt_info = {"ms": oms, "elements": nel, "GBps": (16.0 * nel) / (oms / 1e3) / 1e9,
+                    "what": "global-norm clip (2 B/elem read) + AdamW (14 B/elem) on bf16 LoRA buckets, bf16 moments"}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -323,7 +345,7 @@ def main():
                          "frac": achieved / peaks["sustained"], "traffic": traffic, "launches_timed": n_main,
                          "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
                          "share_of_step": kern_ms / (ms * args.steps) if ms > 0 else None},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "optimizer_step": opt_info,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

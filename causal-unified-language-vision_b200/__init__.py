@@ -9,10 +9,11 @@ hyphens it is imported through the ``b200qlora`` alias module at the repo root
     lora        LoraConfig / LoraLinear4bit / add_adapter / prepare_model_for_kbit_training  (PEFT surface)
     autograd    MatMul4Bit / QLoRALinear autograd Functions
     parallel    GradSync: flat LoRA-gradient buckets + overlapped NCCL all-reduce
+    optim       FusedLoraAdamW: AdamW + global-norm clip over the flat LoRA buckets
     stack       the linear-stack workload used by bench.py
 """
 from . import _lib, functional  # noqa: F401
-from . import autograd, nn, lora, parallel, stack  # noqa: F401,E402
+from . import autograd, nn, lora, parallel, stack, optim  # noqa: F401,E402
 from .functional import QuantState, quantize_4bit, dequantize_4bit  # noqa: F401
 from .nn import Linear4bit, Params4bit  # noqa: F401
 from .lora import LoraConfig, LoraLinear4bit, add_adapter, prepare_model_for_kbit_training  # noqa: F401

@@ -60,6 +60,10 @@ SIGNATURES = {
                                c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "b2q_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2q_reduce_partials": (c_int, [c_void_p, c_int, c_i64, c_float, c_void_p, c_int, c_void_p]),
+    "b2q_sqnorm_blocks": (c_int, [c_i64]),
+    "b2q_sqnorm_partials": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
+    "b2q_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_float, c_float,
+                               c_float, c_i64, c_void_p, c_int, c_float, c_void_p]),
     "b2q_set_variant": (c_int, [c_int, c_int]),
     "b2q_debug_set_trace": (c_int, [c_void_p, c_int]),
     "b2q_debug_set_prefetch": (c_int, [c_int]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb2q.so")
-SOURCES = ["nf4_kernels.cu", "qlora_gemm.cu"]
+SOURCES = ["nf4_kernels.cu", "qlora_gemm.cu", "optim_kernels.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC",

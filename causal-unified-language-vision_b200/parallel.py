@@ -47,6 +47,7 @@ class GradSink:
 class _Bucket:
     flat: torch.Tensor
     members: List[int] = field(default_factory=list)  # slot ids
+    offsets: List[int] = field(default_factory=list)  # element offset of every member inside `flat`
     pending: int = 0
     work: object = None
 
@@ -69,6 +70,7 @@ class GradSync:
             raise ValueError("no LoRA modules")
         device = params[0][1].device
         self.device = device
+        self.slots = params  # (module, parameter, "A" | "B") in backward order; bucket members index into it
         elem = torch.empty(0, dtype=grad_dtype).element_size()
         # bucket assignment
         plan, cur, cur_bytes = [], [], 0
@@ -94,6 +96,7 @@ class GradSync:
                 # keep 16-byte alignment of every view (kernels use 128-bit accesses)
                 assert (off * elem) % 16 == 0
                 view = flat[off:off + prm.numel()].view_as(prm)
+                b.offsets.append(off)
                 off += prm.numel()
                 self._views[(id(mod), which)] = view
                 self._slot_bucket[(id(mod), which)] = len(self.buckets)

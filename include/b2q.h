@@ -153,6 +153,23 @@ int b2q_reduce_partials(const float* partial, int splits, int64_t n, float scale
  * 5: as 3 with a warp-transposed, coalesced-store epilogue [default]); -1 keeps the default / B2Q_*_VARIANT env. */
 int b2q_set_variant(int fwd_variant, int dx_variant);
 
+/* ---- optimizer step on the flat LoRA buckets (the step either side of the path) ------------ *
+ * Replace, for the trainable LoRA parameters, `accel.clip_grad_norm_(model.parameters(), GRAD_MAX)`
+ * (pipeline/CuLLaVOPipeline.py:90-91) and `torch.optim.AdamW(...).step()` (trainer/cullavo_trainer.py:13,
+ * trainer/default_trainer.py:86-90).  Parameters, gradients and (by default) both moments are bf16, as in the
+ * reference after its fp32->bf16 sweep; arithmetic is fp32 per element with one rounding at the end. */
+
+/* Number of fp32 partial sums b2q_sqnorm_partials writes for a buffer of n elements. */
+int b2q_sqnorm_blocks(int64_t n);
+/* partials[b] = sum of g^2 over a fixed slice of the buffer (bit-reproducible). */
+int b2q_sqnorm_partials(const void* g_bf16, int64_t n, float* partials, cudaStream_t stream);
+/* One AdamW step (decoupled weight decay, bias correction for `step` >= 1) on n elements.  When max_norm > 0 the
+ * gradient is first scaled by min(1, max_norm / (sqrt(sum(sq_partials)) + 1e-6)) -- the global-norm clip over ALL
+ * buckets, evaluated on the device (no host synchronisation).  m / v: bf16, or fp32 when state_is_f32. */
+int b2q_adamw_step(void* p_bf16, const void* g_bf16, void* m, void* v, int state_is_f32, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, const float* sq_partials,
+                   int n_partials, float max_norm, cudaStream_t stream);
+
 /* Debug / profiling: when buf != NULL every following tcgen05 GEMM launch records clock64 stamps of its
  * pipeline phases for the first `tiles_per_cta` tiles of every CTA into buf[cta][tile][8] (int64):
  * 0 MMA warp reaches the tile, 1 first operand stage ready, 2/3 accumulator sub-tile 0/1 free, 4 last MMA
