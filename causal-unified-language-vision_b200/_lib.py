@@ -45,6 +45,7 @@ SIGNATURES = {
                                c_int, c_int, c_void_p]),
     "b2q_nf4_quantize": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p]),
     "b2q_absmax_double_quant": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2q_gemv_4bit": (c_int, [c_void_p, ct.POINTER(NF4Weight), c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2q_dropout_mask": (c_int, [c_void_p, c_i64, c_u64, c_float, c_void_p]),
     "b2q_dropout_apply": (c_int, [c_void_p, c_void_p, c_i64, c_u64, c_float, c_void_p]),
     "b2q_dropout_bwd_add": (c_int, [c_void_p, c_void_p, c_i64, c_u64, c_float, c_void_p]),

@@ -50,7 +50,14 @@ class MatMul4Bit(torch.autograd.Function):
 def matmul_4bit(x: torch.Tensor, weight: torch.Tensor, quant_state: F.QuantState,
                 bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``bnb.matmul_4bit(x, W.t(), bias, quant_state)`` equivalent (``weight`` is the packed tensor)."""
-    y = MatMul4Bit.apply(x, weight.data if isinstance(weight, torch.nn.Parameter) else weight, quant_state)
+    packed = weight.data if isinstance(weight, torch.nn.Parameter) else weight
+    rows = x.numel() // x.shape[-1] if x.shape[-1] else 0
+    if 0 < rows <= F.GEMV_MAX_ROWS and not (x.requires_grad and torch.is_grad_enabled()):
+        # bitsandbytes takes its GEMV kernel for single-token inference (no gradient); same rule here
+        x2, lead = _flatten(x)
+        y = F.gemv_4bit(x2, packed, quant_state).reshape(*lead, -1)
+    else:
+        y = MatMul4Bit.apply(x, packed, quant_state)
     if bias is not None:
         y = y + bias.to(y.dtype)
     return y

@@ -47,6 +47,109 @@ __global__ void __launch_bounds__(256) nf4_decode_kernel(const uint32_t* __restr
     }
 }
 
+
+// -------------------------------------------------------------------- GEMV ----
+// y[m, n] = sum_k x[m, k] * dequant(W)[n, k] for a handful of token rows (single-token decoding in `generate`):
+// HBM-bound on the packed weight (N*K/2 bytes), so no tensor cores -- one warp per output row, each lane streams
+// 16 packed bytes (half a quantisation block, one absmax) per step with 128-bit loads, decodes them with the same
+// pre-scaled LUT as the GEMM main loops (bit-identical bf16 weights), accumulates in fp32 and the warp reduces with
+// shuffles.  Replaces bitsandbytes `cgemm_4bit_inference_naive_bf16` (kgemm_4bit_inference_naive).
+template <int MROWS>
+__global__ void __launch_bounds__(128) nf4_gemv_kernel(const __nv_bfloat16* __restrict__ x, const uint4* __restrict__ packed,
+                                                       AbsmaxSrc am, const float* __restrict__ code16_g,
+                                                       __nv_bfloat16* __restrict__ y, int M, int N, int K) {
+    constexpr int RPW = 2;   // output rows per warp: every x chunk fetched from L1 is used for both
+    constexpr int U = 2;     // chunks in flight per lane and row (memory-level parallelism)
+    float code16[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) code16[i] = __ldg(code16_g + i);
+    const int lane = threadIdx.x & 31;
+    const int n0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * RPW;
+    if (n0 >= N) return;
+    const int chunks = K / 32;                       // 16-byte chunks (32 weights) per row
+    float acc[RPW][MROWS];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+        for (int m = 0; m < MROWS; ++m) acc[r][m] = 0.f;
+    // software pipeline: the packed bytes and absmax of batch i+1 are in flight while batch i is decoded
+    uint4 q[RPW][U], qn[RPW][U];
+    float a[RPW][U], an[RPW][U];
+    auto fetch = [&](int c0, uint4 (&qq)[RPW][U], float (&aa)[RPW][U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + 32 * u;
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                const bool ok = c < chunks && n0 + r < N;
+                qq[r][u] = ok ? __ldg(packed + static_cast<long long>(n0 + r) * chunks + c) : make_uint4(0u, 0u, 0u, 0u);
+                aa[r][u] = ok ? load_absmax(am, static_cast<long long>(n0 + r) * (K / 64) + (c >> 1)) : 0.f;
+            }
+        }
+    };
+    fetch(lane, q, a);
+    for (int c0 = lane; c0 < chunks; c0 += 32 * U) {
+        fetch(c0 + 32 * U, qn, an);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + 32 * u;
+            if (c >= chunks) break;
+            uint32_t d[RPW][16];                     // 32 bf16 weights per row, element order
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                Nf4Lut lut;
+                nf4_build_lut(code16, a[r][u], lut);
+                const uint32_t w[4] = {q[r][u].x, q[r][u].y, q[r][u].z, q[r][u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t o[4];
+                    nf4_decode_word(w[j], lut, o);
+                    d[r][4 * j] = o[0]; d[r][4 * j + 1] = o[1]; d[r][4 * j + 2] = o[2]; d[r][4 * j + 3] = o[3];
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < MROWS; ++m) {
+                if (m < M) {
+                    const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<long long>(m) * K + c * 32);
+                    float s[RPW];
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) s[r] = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint4 xv = __ldg(xp + t);
+                        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float xl = __uint_as_float(xw[e] << 16), xh = __uint_as_float(xw[e] & 0xFFFF0000u);
+#pragma unroll
+                            for (int r = 0; r < RPW; ++r) {
+                                const uint32_t wv = d[r][4 * t + e];
+                                s[r] = fmaf(__uint_as_float(wv << 16), xl, s[r]);
+                                s[r] = fmaf(__uint_as_float(wv & 0xFFFF0000u), xh, s[r]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) acc[r][m] += s[r];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) { q[r][u] = qn[r][u]; a[r][u] = an[r][u]; }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+        for (int m = 0; m < MROWS; ++m) {
+            float v = acc[r][m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && m < M && n0 + r < N) y[static_cast<long long>(m) * N + n0 + r] = __float2bfloat16_rn(v);
+        }
+}
+
 // ---------------------------------------------------------------- quantise ----
 __device__ __forceinline__ uint32_t nf4_code_of(float x) {
     // number of thresholds strictly below x (== bitsandbytes' dQuantizeNF4 comparison tree); NaN -> 0
@@ -238,6 +341,27 @@ extern "C" int b2q_nf4_decode(const uint8_t* packed, const float* absmax, const 
     else
         nf4_decode_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(packed), am, code16,
                                                        reinterpret_cast<uint4*>(out_bf16), n_words);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+
+extern "C" int b2q_gemv_4bit(const void* x_bf16, const b2q_nf4_weight* w, void* y_bf16, int M, int N, int K,
+                             cudaStream_t stream) {
+    if (M == 0) return 0;
+    if (x_bf16 == nullptr || y_bf16 == nullptr || w == nullptr || w->packed == nullptr || w->code16 == nullptr)
+        return B2Q_ERR_ARG;
+    if (w->absmax_q == nullptr && w->absmax == nullptr) return B2Q_ERR_ARG;
+    if (M < 0 || M > 8 || K % 64 != 0 || N <= 0) return B2Q_ERR_SHAPE;
+    if (((reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(w->packed)) & 15) != 0) return B2Q_ERR_ARG;
+    AbsmaxSrc am{w->absmax, w->absmax_q, w->absmax2, w->code256, w->offset};
+    const int grid = (N + 7) / 8;   // 4 warps x 2 rows per block
+    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
+    __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
+    const uint4* pk = reinterpret_cast<const uint4*>(w->packed);
+    if (M == 1) nf4_gemv_kernel<1><<<grid, 128, 0, stream>>>(x, pk, am, w->code16, y, M, N, K);
+    else if (M <= 4) nf4_gemv_kernel<4><<<grid, 128, 0, stream>>>(x, pk, am, w->code16, y, M, N, K);
+    else nf4_gemv_kernel<8><<<grid, 128, 0, stream>>>(x, pk, am, w->code16, y, M, N, K);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

@@ -225,6 +225,26 @@ def dequantize_4bit(A: torch.Tensor, quant_state: QuantState, algo: int = 1) -> 
     return out
 
 
+GEMV_MAX_ROWS = 8
+
+
+def gemv_4bit(x: torch.Tensor, packed: torch.Tensor, qs: QuantState) -> torch.Tensor:
+    """y = x @ dequant(W)^T for up to 8 token rows (inference / `generate`): HBM-bound SIMT kernel, no tensor cores.
+    Stand-in for ``bitsandbytes.functional.gemv_4bit``."""
+    _need_cuda(x, packed)
+    _need(x, torch.bfloat16, "x")
+    M, K = x.shape
+    N = int(qs.shape[0])
+    if int(qs.shape[1]) != K:
+        raise ValueError(f"x has {K} features, weight expects {int(qs.shape[1])}")
+    if M > GEMV_MAX_ROWS:
+        raise ValueError(f"gemv_4bit handles at most {GEMV_MAX_ROWS} rows, got {M}")
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    w = qs.c_weight(packed)
+    _lib.check(_lib.load().b2q_gemv_4bit(_p(x), ct.byref(w), _p(y), M, N, K, _stream()), "b2q_gemv_4bit")
+    return y
+
+
 # ------------------------------------------------------------------------------ dropout ----
 def dropout_mask(shape, seed: int, p: float, device) -> torch.Tensor:
     mask = torch.empty(shape, dtype=torch.uint8, device=device)

@@ -83,6 +83,12 @@ int b2q_nf4_quantize(const void* w, int w_is_bf16, int64_t n, uint8_t* packed, f
 int b2q_absmax_double_quant(const float* absmax, int64_t nblocks, const float* code256, uint8_t* absmax_q,
                             float* absmax2, float* offset_out, cudaStream_t stream);
 
+/* y[M,N] = x[M,K] @ dequant(W)^T for M <= 8 token rows (bf16 in / out, fp32 accumulate): the single-token decoding
+ * path of `generate` (cullavo/arch_cullavo.py:364-365).  HBM-bound on the packed weight, SIMT + warp shuffles, same
+ * bit-exact decode as the GEMMs.  Replaces bitsandbytes `cgemm_4bit_inference_naive_bf16`, which
+ * `bnb.matmul_4bit` selects when the input is one token and needs no gradient.  Contract: K % 64 == 0. */
+int b2q_gemv_4bit(const void* x_bf16, const b2q_nf4_weight* w, void* y_bf16, int M, int N, int K, cudaStream_t stream);
+
 /* ---- LoRA-branch dropout (PEFT `lora_dropout`, cullavo/load_cullavo.py:98,107) ---------- */
 
 /* mask[i] = keep(seed, i) in {0,1};  keep is a counter-based hash so forward, backward and the

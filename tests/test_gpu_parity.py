@@ -326,7 +326,7 @@ def test_empty_fp32_and_strided_inputs(F, cuda_dev):
     # shapes outside the kernel contract fail loudly instead of silently falling back
     bad = stackmod.make_quantized_linear(192, 256, cuda_dev, gen)   # N % 256 != 0
     with pytest.raises(RuntimeError):
-        bad(torch.randn(4, 256, device=cuda_dev, dtype=torch.bfloat16))
+        bad(torch.randn(64, 256, device=cuda_dev, dtype=torch.bfloat16))
 
 
 def test_checkpoint_recompute_reproduces_dropout_mask(F, cuda_dev):
@@ -361,3 +361,30 @@ def test_checkpoint_recompute_reproduces_dropout_mask(F, cuda_dev):
     b = run(True)
     for t0, t1 in zip(a, b):
         assert torch.equal(t0, t1)
+
+
+@pytest.mark.parametrize("M,N,K,dq", [(1, 4096, 4096, True), (3, 1024, 4096, False), (8, 4096, 11008, True), (1, 256, 64, True)])
+def test_gemv_single_token_path(F, cuda_dev, M, N, K, dq):
+    """`generate`'s single-token path: y = x @ dequant(W)^T, HBM-bound GEMV kernel."""
+    from oracle import nf4
+    from oracle.qlora import rel_err
+
+    rng = np.random.default_rng(N + K)
+    st = nf4.quantize_nf4(rng.normal(0, 0.02, (N, K)).astype(np.float32), 64, dq)
+    packed, qs = _state_to_gpu(st, cuda_dev)
+    x = torch.from_numpy(rng.normal(0, 1, (M, K)).astype(np.float32)).bfloat16()
+    W = torch.from_numpy(nf4.dequantize_nf4(st, as_bits=False).copy()).float()
+    ref = (x.float() @ W.t()).bfloat16()
+    y = F.gemv_4bit(x.to(cuda_dev), packed, qs)
+    assert rel_err(y.cpu(), ref) <= 1e-2
+    # the module takes this path on its own for <= 8 rows without gradient, and agrees with the tensor-core path
+    if N % 256 == 0:
+        y_gemm = F.qlora_fwd(x.to(cuda_dev), packed, qs, None, None)
+        assert rel_err(y.cpu(), y_gemm.cpu()) <= 1e-2
+        stackmod = importlib.import_module("causal-unified-language-vision_b200.stack")
+        lin = stackmod.make_quantized_linear(N, K, cuda_dev, torch.Generator(device=cuda_dev).manual_seed(0))
+        launches = F.launch_count()
+        with torch.no_grad():
+            out = lin(x.to(cuda_dev))
+        assert F.launch_count() - launches == 1 and out.shape == (M, N)
+        assert rel_err(out.cpu(), F.qlora_fwd(x.to(cuda_dev), lin.weight.data, lin.weight.quant_state, None, None).cpu()) <= 1e-2
