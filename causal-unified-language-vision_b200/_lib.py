@@ -12,7 +12,8 @@ import ctypes as ct
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2q.so")
+# B2Q_LIB_PATH: development hook for same-box A/B runs of two builds of the library (never a fallback)
+LIB_PATH = os.environ.get("B2Q_LIB_PATH") or os.path.join(_HERE, "libb2q.so")
 
 c_void_p = ct.c_void_p
 c_int = ct.c_int

@@ -121,9 +121,43 @@ static int num_sms() {
     return n;
 }
 
+// Row stride of the 128-row tiles of a skinny kernel such that one wave covers the SMs as evenly as possible
+// (M = 16384 -> 147 tiles of 112 rows instead of 128 tiles on 148 SMs).  Strides below 96 rows are not worth
+// the redundant operand rows.
+static int balanced_tile_rows(int rows) {
+    const int sms = num_sms();
+    int best = 128;
+    long long best_waves = (static_cast<long long>((rows + 127) / 128) + sms - 1) / sms;
+    for (int t = 120; t >= 96; t -= 8) {
+        const long long waves = (static_cast<long long>((rows + t - 1) / t) + sms - 1) / sms;
+        if (waves < best_waves) { best_waves = waves; best = t; }
+    }
+    return best;
+}
+
+struct GradPlan { int tile, splits; };
+// (tile stride, split-M factor) of a LoRA-gradient GEMM with `rows` output rows and `kblocks` 64-token k-blocks
+static GradPlan grad_plan(int rows, int kblocks) {
+    const int sms = num_sms();
+    GradPlan best{128, 1};
+    double best_cost = 1e30;
+    for (int t = 128; t >= 96; t -= 8) {
+        const int tiles = (rows + t - 1) / t;
+        int s = sms / (tiles > 0 ? tiles : 1);
+        if (s < 1) s = 1;
+        if (s > kblocks) s = kblocks > 0 ? kblocks : 1;
+        if (s > 32) s = 32;
+        const long long ctas = static_cast<long long>(tiles) * s;
+        const double cost = static_cast<double>((ctas + sms - 1) / sms) * ((kblocks + s - 1) / s);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = GradPlan{t, s}; }
+    }
+    return best;
+}
+
 static long long* g_trace = nullptr;   // debug: phase trace buffer for the next launches (b2q_debug_set_trace)
 static int g_trace_tiles = 0;
 static int g_pf_dist = 0;
+static int g_pdl = -1;   // -1: read B2Q_PDL (default on)
 
 template <class Cfg>
 static int launch(GemmParams& p, cudaStream_t stream) {
@@ -134,10 +168,12 @@ static int launch(GemmParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
+    if (g_pdl < 0) { const char* v = getenv("B2Q_PDL"); g_pdl = v ? atoi(v) : 1; }
     p.trace = g_trace;
     p.trace_tiles = g_trace_tiles;
     p.pf_dist = g_pf_dist;
-    p.m_tiles = (p.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+    if (p.tile_m <= 0 || p.tile_m > Cfg::TILE_M || Cfg::EPI_COAL || Cfg::EPI_TMA) p.tile_m = Cfg::TILE_M;
+    p.m_tiles = (p.M + p.tile_m - 1) / p.tile_m;
     p.n_tiles = (p.N + Cfg::BN - 1) / Cfg::BN;
     if (p.group_m <= 0) p.group_m = p.m_tiles;
     const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
@@ -149,13 +185,16 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attrs[1];
+    cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
     attrs[0].val.clusterDim.x = Cfg::CG;
     attrs[0].val.clusterDim.y = 1;
     attrs[0].val.clusterDim.z = 1;
+    // programmatic dependent launch: the prologue of this grid overlaps the tail of the previous kernel in the stream
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_pdl ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, qlora_gemm_kernel<Cfg>, p);
     count_launch();
     return static_cast<int>(e);
@@ -200,12 +239,13 @@ using DxV4 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, 1>;
 using FwdV5 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, -1>;
 using DxV5 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, -1>;
 
-template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, 6>;   // u = x A^T
-template <int R> using DownDropCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, 6, 0, 0, true>;   // u = drop(x) A^T
+template <int R> constexpr int skinny_stages() { return 6; }
+template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>()>;   // u = x A^T
+template <int R> using DownDropCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>(), 0, 0, true>;   // u = drop(x) A^T
 template <int R> using GradADropCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true>;
 // dx += keep * (du A) / (1 - p): masked epilogue, TMA reduce-add into dx (dropout backward)
 using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 5, 0, 0, false, 1>;
-template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, 6>;      // du = s dy B
+template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, skinny_stages<R>()>;      // du = s dy B
 template <int R> using GradACfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6>;  // dA^T tile, stored transposed
 template <int R> using GradBCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART, 6>;    // dB tile
 using GemmKN = GemmCfg<1, 1, 128, false, true, false, EPI_BF16, 6>;   // b given [K,N]
@@ -354,6 +394,7 @@ static int lora_down_r(const void* x, const void* lora_A, float scale, uint64_t 
     const float keep_scale = 1.0f / (1.0f - drop_p);
     p.D = u; p.D2 = us; p.ldd = R; p.alpha = keep_scale; p.alpha2 = scale * keep_scale;
     p.M = M; p.N = R; p.kb_main = K / 64; p.kb_tail = 0; p.splits = 1;
+    p.tile_m = balanced_tile_rows(M);
     p.seed = seed; p.thresh16 = dropout_threshold(drop_p); p.xf_ld = K;
     int e;
     if ((e = map_bf16_kmajor(&p.tmA, x, M, K, 128))) return e;
@@ -379,6 +420,7 @@ static int lora_du_r(const void* dy, const void* lora_B, float scale, void* du, 
     memset(&p, 0, sizeof(p));
     p.D = du; p.D2 = nullptr; p.ldd = R; p.alpha = scale;
     p.M = M; p.N = R; p.kb_main = N / 64; p.kb_tail = 0; p.splits = 1;
+    p.tile_m = balanced_tile_rows(M);
     int e;
     if ((e = map_bf16_kmajor(&p.tmA, dy, M, N, 128))) return e;
     if ((e = map_bf16_mnmajor(&p.tmB, lora_B, N, R))) return e;  // lora_B [N][r]: contraction rows, r contiguous
@@ -395,18 +437,10 @@ extern "C" int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, 
     return B2Q_ERR_SHAPE;
 }
 
-static int grad_splits(int out_tiles, int kblocks) {
-    int s = num_sms() / (out_tiles > 0 ? out_tiles : 1);
-    if (s < 1) s = 1;
-    if (s > kblocks) s = kblocks > 0 ? kblocks : 1;
-    if (s > 32) s = 32;
-    return s;
-}
-
 extern "C" size_t b2q_lora_grads_workspace_bytes(int M, int N, int K, int r) {
     const int kblocks = (M + 63) / 64;
-    const size_t a = static_cast<size_t>(grad_splits(K / 128, kblocks)) * r * K * sizeof(float);
-    const size_t b = static_cast<size_t>(grad_splits(N / 128, kblocks)) * N * r * sizeof(float);
+    const size_t a = static_cast<size_t>(grad_plan(K, kblocks).splits) * r * K * sizeof(float);
+    const size_t b = static_cast<size_t>(grad_plan(N, kblocks).splits) * N * r * sizeof(float);
     return a + b + 256;
 }
 
@@ -417,12 +451,14 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
     const int kblocks = (M + 63) / 64;
     int e;
     // dA^T[k, j] = sum_m xd[m, k] * du[m, j]   (A = xd^T MN-major, B = du MN-major), stored transposed -> [r][K]
-    const int sa = grad_splits(K / 128, kblocks);
+    const GradPlan pa = grad_plan(K, kblocks);
+    const int sa = pa.splits;
     float* wa = ws;
     {
         GemmParams p;
         memset(&p, 0, sizeof(p));
         p.D = wa; p.M = K; p.N = R; p.splits = sa; p.kb_main = (kblocks + sa - 1) / sa; p.kb_tail = 0;
+        p.tile_m = pa.tile;
         p.seed = seed; p.thresh16 = dropout_threshold(drop_p); p.xf_ld = K;
         if ((e = map_bf16_mnmajor(&p.tmA, xd, M, K))) return e;
         if ((e = map_bf16_mnmajor(&p.tmB, du, M, R))) return e;
@@ -433,12 +469,14 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
             return e;
     }
     // dB[n, j] = scale * sum_m dy[m, n] * u[m, j]
-    const int sb = grad_splits(N / 128, kblocks);
+    const GradPlan pb = grad_plan(N, kblocks);
+    const int sb = pb.splits;
     float* wb = ws + static_cast<size_t>(sa) * R * K;
     {
         GemmParams p;
         memset(&p, 0, sizeof(p));
         p.D = wb; p.M = N; p.N = R; p.splits = sb; p.kb_main = (kblocks + sb - 1) / sb; p.kb_tail = 0;
+        p.tile_m = pb.tile;
         if ((e = map_bf16_mnmajor(&p.tmA, dy, M, N))) return e;
         if ((e = map_bf16_mnmajor(&p.tmB, u, M, R))) return e;
         if ((e = launch<GradBCfg<R>>(p, stream))) return e;

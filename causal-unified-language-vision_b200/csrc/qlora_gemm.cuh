@@ -57,6 +57,8 @@ struct GemmParams {
     int kpr;           // absmax blocks per W row (= K_w / 64)          (B_DEC)
     int m_tiles, n_tiles;
     int group_m;       // rasterisation: m-tiles per L2 slab
+    int tile_m;        // row stride between m-tiles, <= TILE_M (load-balancing of the skinny kernels: a tile still
+                       // loads and multiplies TILE_M rows, but only stores its first tile_m -- the rest belong to the next tile)
     int accum_d;       // EPI_BF16: D = bf16(D + alpha * acc)  (read-modify-write of the caller's buffer)
     // LoRA dropout (A_XF transform / EPI_BF16_MASK): keep(i) for element i = row * xf_ld + col of the
     // activation the mask belongs to (b2q_internal.h dropout_keep)
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             mbar_init(empty_bar(s), 1);                   // tcgen05.commit
         }
         if constexpr (Cfg::A_XF)
-            for (int s = 0; s < STAGES; ++s) mbar_init(xf_bar(s), Cfg::XF_THREADS / 32);  // one arrive per transform warp
+            for (int s = 0; s < STAGES; ++s) mbar_init(xf_bar(s), Cfg::XF_THREADS / 64);  // one arrive per warp of the owning group
         for (int s = 0; s < PST; ++s) {
             mbar_init(pk_bar(s), 1);                      // packed-ring producer (+tx)
             mbar_init(pk_empty_bar(s), Cfg::NDW);         // decode warps, once the bytes are in registers
@@ -209,6 +211,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish<CG>();
     }
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run
+    // while the previous kernel of the stream is still draining; nothing below touches global memory before the
+    // previous grid has completed and flushed.  Dependents of THIS grid may be scheduled as soon as SMs free up.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if constexpr (Cfg::B_DEC) {
         if (p.am.absmax_q != nullptr)
             for (int i = threadIdx.x; i < 256; i += Cfg::THREADS) code256_s[i] = __ldg(p.am.code256 + i);
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
                 int mt_i, nt_i, split;
                 tile_coords(p, tile, mt_i, nt_i, split);
-                const int m0 = mt_i * Cfg::TILE_M;
+                const int m0 = mt_i * p.tile_m;
                 const int n0 = nt_i * BN;
                 const int kb0 = split * p.kb_main;
                 for (int kb = 0; kb < kb_total; ++kb) {
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tseq) {
             int mt_i, nt_i, split;
             tile_coords(p, tile, mt_i, nt_i, split);
-            const int m0 = mt_i * Cfg::TILE_M;
+            const int m0 = mt_i * p.tile_m;
             const int n0 = nt_i * BN;
             long long* tr = (p.trace != nullptr && tseq < p.trace_tiles && wq == 0 && lane == 0)
                                 ? p.trace + (static_cast<long long>(blockIdx.x) * p.trace_tiles + tseq) * 8 : nullptr;
@@ -414,13 +421,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     if constexpr (Cfg::EPI == EPI_BF16_MASK) {
                         // LoRA-dropout backward: zero the dropped elements (element index = row * xf_ld + col)
                         const unsigned long long e0 = static_cast<unsigned long long>(row_t + lane) * p.xf_ld + (n0 + c * 64);
-                        const uint32_t j0 = static_cast<uint32_t>(e0 >> 1);
+                        const uint32_t j0 = static_cast<uint32_t>(e0 >> 2);
                         const uint32_t s_lo = static_cast<uint32_t>(p.seed), s_hi = static_cast<uint32_t>(p.seed >> 32);
                         const uint32_t thr = p.thresh16;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const uint32_t h = dropout_hash32(s_lo, s_hi, j0 + j);
-                            o[j] &= ((h & 0xFFFFu) >= thr ? 0x0000FFFFu : 0u) | ((h >> 16) >= thr ? 0xFFFF0000u : 0u);
+                        for (int j = 0; j < 16; ++j) {   // one 64-bit hash per four elements (two packed words)
+                            uint32_t ha, hb;
+                            dropout_hash64(s_lo, s_hi, j0 + j, ha, hb);
+                            o[2 * j] &= dropout_mask2(ha, thr);
+                            o[2 * j + 1] &= dropout_mask2(hb, thr);
                         }
                     }
                     if (c == GPM - 1) {   // sub-tile mt drained: its last TMEM load has completed
@@ -502,21 +511,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     tmem_ld_32x32(t_row + c * 32, v);
                     tmem_ld_wait();
                     const int col0 = n0 + c * 32;
-                    if (row < p.M && col0 < p.N) {
+                    if (row < p.M && row - m0 < p.tile_m && col0 < p.N) {
                         if constexpr (Cfg::EPI == EPI_BF16 || Cfg::EPI == EPI_BF16_MASK) {
                             uint32_t o[16];
                             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) +
                                                                   static_cast<long long>(row) * p.ldd + col0);
                             if constexpr (Cfg::EPI == EPI_BF16_MASK) {
                                 const unsigned long long e0 = static_cast<unsigned long long>(row) * p.xf_ld + col0;
-                                const uint32_t j0 = static_cast<uint32_t>(e0 >> 1);
+                                const uint32_t j0 = static_cast<uint32_t>(e0 >> 2);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const uint32_t h = dropout_hash32(static_cast<uint32_t>(p.seed),
-                                                                      static_cast<uint32_t>(p.seed >> 32), j0 + j);
-                                    const float lo = (h & 0xFFFFu) >= p.thresh16 ? __uint_as_float(v[2 * j]) * p.alpha : 0.f;
-                                    const float hi = (h >> 16) >= p.thresh16 ? __uint_as_float(v[2 * j + 1]) * p.alpha : 0.f;
-                                    o[j] = pack_bf16x2(lo, hi);
+                                for (int j = 0; j < 8; ++j) {
+                                    uint32_t ha, hb;
+                                    dropout_hash64(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32), j0 + j, ha, hb);
+                                    o[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) * p.alpha, __uint_as_float(v[4 * j + 1]) * p.alpha) &
+                                               dropout_mask2(ha, p.thresh16);
+                                    o[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) * p.alpha, __uint_as_float(v[4 * j + 3]) * p.alpha) &
+                                                   dropout_mask2(hb, p.thresh16);
                                 }
                             } else if (p.accum_d) {
 #pragma unroll
@@ -580,23 +590,28 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
       if constexpr (Cfg::A_XF) {
         // ============================================ A-operand transform ====
         // LoRA dropout: zero the dropped elements of the A tile in place (the 1/(1-p) scale is folded
-        // into the epilogue).  256 threads, four 16-byte chunks (8 bf16) each per stage; chunk q sits
-        // at byte q*16 of the stage: row q>>3, physical chunk q&7 holds logical chunk (q&7)^(row&7).
-        const int t = threadIdx.x - 256;
+        // into the epilogue).  Two groups of 128 threads take ring positions alternately, so two stages are
+        // being transformed at any time (one group alone is latency-bound: barrier wake-up, LDS, hash, STS,
+        // proxy fence, arrive per stage).  A thread handles eight 16-byte chunks (8 bf16 each) of its stage;
+        // chunk q sits at byte q*16: row q>>3, physical chunk q&7 holds logical chunk (q&7)^(row&7).
+        constexpr int XG = 2, XT = Cfg::XF_THREADS / XG;
+        const int g = (threadIdx.x - 256) / XT;
+        const int t = (threadIdx.x - 256) % XT;
         const uint32_t seed_lo = static_cast<uint32_t>(p.seed), seed_hi = static_cast<uint32_t>(p.seed >> 32);
-        int s = 0;
-        uint32_t ph = 0;
+        const uint32_t thr = p.thresh16;
+        uint32_t it = 0;   // ring position over all k-blocks of all tiles
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
             int mt_i, nt_i, split;
             tile_coords(p, tile, mt_i, nt_i, split);
-            const int row0 = mt_i * Cfg::TILE_M;
+            const int row0 = mt_i * p.tile_m;
             const int kb0 = split * p.kb_main;
-            for (int kb = 0; kb < kb_total; ++kb) {
+            for (int kb = static_cast<int>((static_cast<uint32_t>(g) - it) & (XG - 1)); kb < kb_total; kb += XG) {
                 const int k0 = (kb0 + kb) * 64;
+                const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
                 mbar_wait(full_bar(s), ph);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = t + 256 * i;
+                for (int i = 0; i < 1024 / XT; ++i) {
+                    const int q = t + XT * i;
                     const int rr = (q >> 3) & 63, cl = (q & 7) ^ (rr & 7);
                     long long e0;
                     if constexpr (!Cfg::A_MN) {   // rows = MN coordinate, 64 contraction elements per row
@@ -605,17 +620,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     } else {                      // rows = contraction coordinate, two boxes of 64 MN elements
                         e0 = static_cast<long long>(k0 + rr) * p.xf_ld + row0 + (q >> 9) * 64 + cl * 8;
                     }
-                    const uint32_t j0 = static_cast<uint32_t>(static_cast<unsigned long long>(e0) >> 1);
+                    const uint32_t j0 = static_cast<uint32_t>(static_cast<unsigned long long>(e0) >> 2);
                     const uint32_t addr = a_stage(s) + q * 16;
                     uint32_t w[4];
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t h = dropout_hash32(seed_lo, seed_hi, j0 + j);
-                        const uint32_t m = ((h & 0xFFFFu) >= p.thresh16 ? 0x0000FFFFu : 0u) |
-                                           ((h >> 16) >= p.thresh16 ? 0xFFFF0000u : 0u);
-                        w[j] &= m;
+                    for (int j = 0; j < 2; ++j) {   // 8 elements = two 64-bit hashes
+                        uint32_t ha, hb;
+                        dropout_hash64(seed_lo, seed_hi, j0 + j, ha, hb);
+                        w[2 * j] &= dropout_mask2(ha, thr);
+                        w[2 * j + 1] &= dropout_mask2(hb, thr);
                     }
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                                  "r"(w[3]) : "memory");
@@ -623,8 +638,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(xf_bar(s));
-                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
+            it += kb_total;
         }
       }
       if constexpr (Cfg::B_DEC) {

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--variants", default="0,1,2,3")
     ap.add_argument("--shapes", default="4096x4096,14336x4096,4096x14336")
     ap.add_argument("--r", type=int, default=64)
+    ap.add_argument("--skinny-only", action="store_true", help="only the HBM-bound LoRA kernels (with and without dropout)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_bench.jsonl"))
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -79,6 +80,14 @@ def main():
         dB = torch.zeros(N, r, device=dev, dtype=torch.bfloat16)
         med, best = timeit(lambda: F.lora_grads(dy, x, u, du, 0.25, dA, dB))
         emit(kernel="lora_grads", N=N, K=K, M=M, ms=med, gbs=(2.0 * M * (N + K)) / med / 1e6)
+        med, best = timeit(lambda: F.lora_down(x, A, 0.25, 99, 0.05))
+        emit(kernel="lora_down_drop", N=N, K=K, M=M, ms=med, gbs=(2.0 * M * K) / med / 1e6)
+        med, best = timeit(lambda: F.lora_grads(dy, x, u, du, 0.25, dA, dB, seed=99, p=0.05))
+        emit(kernel="lora_grads_drop", N=N, K=K, M=M, ms=med, gbs=(2.0 * M * (N + K)) / med / 1e6)
+        if args.skinny_only:
+            del x, dy, Wb, packed
+            torch.cuda.empty_cache()
+            continue
         for v in (int(s) for s in args.variants.split(",")):
             F.set_variant(v, v)
             for lora in (False, True):

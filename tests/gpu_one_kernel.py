@@ -10,7 +10,7 @@ import b200qlora as q  # noqa: E402
 
 F = q.functional
 which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
-variant = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+variant = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 M, N, K = (int(v) for v in sys.argv[3:6]) if len(sys.argv) > 5 else (16384, 4096, 4096)
 lora = len(sys.argv) > 6 and sys.argv[6] == "lora"
 dev = torch.device("cuda:0")
