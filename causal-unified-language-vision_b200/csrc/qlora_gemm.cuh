@@ -265,10 +265,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     }
                     if constexpr (!Cfg::A_MN) {
                         // pull the A tile of k-block kb + pf_dist into L2 now, so that its TMA load is an L2 hit
-                        if ((p.pf_dist & 0xff) > 0 && !tail && kb + (p.pf_dist & 0xff) < p.kb_main) {
+                        if (p.pf_dist > 0 && !tail && kb + p.pf_dist < p.kb_main) {
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt)
-                                tma_prefetch_2d(mapA, k0 + (p.pf_dist & 0xff) * 64,
+                                tma_prefetch_2d(mapA, k0 + p.pf_dist * 64,
                                                 m0 + (CG == 2 ? mt * 256 + static_cast<int>(rank) * 128 : mt * 128));
                         }
                     }
@@ -699,16 +699,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);              // decoded-B slot free (MMAs that read it retired)
                 const uint32_t dst = b_stage(s) + dst_off;
-                if (!(p.pf_dist & 0x400)) {   // debug bit 0x400: no decode at all (timing experiments only)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     uint32_t o[4];
                     nf4_decode_word(w[j], lut, o);
-                    if (!(p.pf_dist & 0x200))   // debug bit 0x200: decode but do not store
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + ((static_cast<uint32_t>(j) ^ key) << 4)),
                                  "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                    else if (o[0] == 0x12345678u && o[3] == 0x9abcdef0u) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst), "r"(o[1]) : "memory");
-                }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
