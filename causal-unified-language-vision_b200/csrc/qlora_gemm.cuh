@@ -4,13 +4,16 @@
 //   D[M,N] = sum over main k-blocks  A[M, 64] * Bop[64, N]      (Bop: bf16 via TMA, or NF4 decoded)
 //          + sum over tail k-blocks  A2[M, 64] * B2[64, N]      (LoRA tail, bf16 via TMA)
 //
-// Roles (one CTA per SM, or a CTA pair with cta_group::2):
-//   warp 0      TMA producer (A, TMA-fed B)   warp 1   UMMA issuer (leader CTA only)
-//   warp 2      TMEM allocator                warp 3   TMA producer of the packed-NF4 ring (B_DEC)
-//   warps 4-7   epilogue (TMEM -> registers -> global)
-//   warps 8..   NF4 decode (B_DEC), NG groups of BNC threads taking k-blocks round-robin:
+// Roles (one CTA per SM, or a CTA pair with cta_group::2); warp ids are GemmCfg::W_*:
+//   TMA producer (A, TMA-fed B)      UMMA issuer (one thread of the leader CTA)      TMEM allocator
+//   TMA producer of the packed-NF4 ring (B_DEC)
+//   warps 4-7   epilogue (TMEM -> registers -> shared-memory staging -> global)
+//   NF4 decode (B_DEC): 8 warps = NG groups of BNC threads taking k-blocks round-robin:
 //               packed bytes (TMA-staged smem) -> registers (LUT/PRMT) -> bf16 in the canonical
 //               128B-swizzled UMMA operand layout in smem
+//   warps 8..   (A_XF) in-shared-memory LoRA-dropout transform of the A tile
+// In the decode kernels the warp ids are chosen so that no decode warp shares a warp scheduler (id % 4) with the UMMA
+// issuer: see the role map in GemmCfg.
 //
 // Shared memory: STAGES x {A tile (MT x 128 rows x 64 k bf16), B tile (BNC rows x 64 k bf16)}
 // plus an independent, deeper ring of PST packed-NF4 tiles (BNC x 32 B) so the packed bytes are
@@ -110,8 +113,18 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                      : TMEM_COLS_RAW <= 256 ? 256 : 512;
     static constexpr int NDT = B_DEC ? BNC : 0;         // decode threads per group
-    static constexpr int NDW = NDT / 32;                // decode warps per group (arrivals per stage)
+    static constexpr int NDW = NDT / 32;                // working decode warps per group (arrivals per stage)
+    // Role -> warp id.  A warp's scheduler (SM sub-partition) is warp id % 4.  In the decode kernels every warp whose id
+    // is 1 (mod 4) is a light or main-loop-idle role -- the single-thread UMMA issuer (1), an epilogue warp (5), the
+    // operand TMA producer (9), the packed-ring producer + TMEM allocator (13) -- and the 8 decode warps take the ids
+    // {0, 2, 3, 8, 10, 11, 12, 14}: ALU-heavy decode warps on the issuer's scheduler delay its instruction issue enough
+    // to cost the main loop 13 % of its MMA rate (phase-trace experiment).
+    static constexpr int W_PROD = B_DEC ? 9 : 0;
+    static constexpr int W_MMA = 1;
+    static constexpr int W_ALLOC = B_DEC ? 13 : 2;
+    static constexpr int W_PACK = B_DEC ? 13 : -1;
     static constexpr int THREADS = 256 + NG * NDT + XF_THREADS;
+    static_assert(!B_DEC || NG * NDT == 256, "decode role map assumes 8 decode warps");
     static_assert(!(A_XF_ && B_DEC_), "A transform and B decode share the warps 8+");
     static_assert(!A_XF_ || (MT_ == 1 && CG_ == 1), "A transform: single 128-row tile, single CTA");
     static constexpr int BAR_BYTES = 1024;              // barriers + tmem ptr + code256
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     const int kb_total = p.kb_main + p.kb_tail;
 
     // ---------------------------------------------------------------- setup ----
-    if (warp == 0 && lane == 0) {
+    if (warp == Cfg::W_PROD && lane == 0) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         if (p.kb_tail > 0) {
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         }
         if constexpr (Cfg::EPI_TMA) tma_prefetch_desc(&p.tmD);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == Cfg::W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), CG * (1 + Cfg::NDW));  // per CTA: producer (+tx) + one arrive per decode warp
             mbar_init(empty_bar(s), 1);                   // tcgen05.commit
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         }
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == Cfg::W_ALLOC) {
         tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish<CG>();
     }
@@ -229,7 +242,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     auto full_bar_arrive = [&](int s) { return CG == 2 ? mapa(full_bar(s), 0) : full_bar(s); };
     auto tempty_bar_arrive = [&](int a, int mt) { return CG == 2 ? mapa(tempty_bar(a, mt), 0) : tempty_bar(a, mt); };
 
-    if (warp == 0) {
+    if (warp == Cfg::W_PROD) {
         // ===================================================== TMA producer ====
         if (lane == 0) {
             int s = 0;
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == Cfg::W_MMA) {
         // ====================================================== UMMA issuer ====
         if (rank == 0 && lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, BN, Cfg::A_MN ? 1 : 0, Cfg::B_MN ? 1 : 0);
@@ -313,6 +326,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     mbar_wait(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph);
                     tc_fence_after();
                     if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
+                    const uint64_t a_base = Cfg::A_MN ? umma_desc_sw128(a_stage(s), 8192, 1024) : umma_desc_sw128(a_stage(s), 16, 1024);
+                    const uint64_t b_base = Cfg::B_MN ? umma_desc_sw128(b_stage(s), 8192, 1024) : umma_desc_sw128(b_stage(s), 16, 1024);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
@@ -322,13 +337,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                             if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
                         }
                         const uint32_t d_tmem = tmem_base + as * ACC_COLS + mt * BN;
+                        // descriptors of (stage, mt, k) = descriptor of the stage base + a constant in the address field
+                        // (the stage bases are 1024-byte aligned and the offsets stay far below the 14-bit field)
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t adesc =
-                                Cfg::A_MN ? umma_desc_sw128(a_stage(s) + mt * 16384 + k * 2048, 8192, 1024)
-                                          : umma_desc_sw128(a_stage(s) + mt * 16384 + k * 32, 16, 1024);
-                            const uint64_t bdesc = Cfg::B_MN ? umma_desc_sw128(b_stage(s) + k * 2048, 8192, 1024)
-                                                             : umma_desc_sw128(b_stage(s) + k * 32, 16, 1024);
+                            const uint64_t adesc = a_base + static_cast<uint64_t>((mt * 16384 + k * (Cfg::A_MN ? 2048 : 32)) >> 4);
+                            const uint64_t bdesc = b_base + static_cast<uint64_t>((k * (Cfg::B_MN ? 2048 : 32)) >> 4);
                             umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         }
                     }
@@ -342,7 +356,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
             }
         }
-    } else if (Cfg::B_DEC && warp == 3) {
+    } else if (Cfg::B_DEC && warp == Cfg::W_PACK) {
         // ================================== TMA producer, packed-NF4 ring ====
         if (lane == 0) {
             int ps = 0;
@@ -586,7 +600,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         if constexpr (Cfg::EPI_TMA) {
             if (lane == 0) tma_store_wait<0>();   // all bulk stores of this warp are complete before the CTA exits
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 || Cfg::B_DEC) {
       if constexpr (Cfg::A_XF) {
         // ============================================ A-operand transform ====
         // LoRA dropout: zero the dropped elements of the A tile in place (the 1/(1-p) scale is folded
@@ -646,8 +660,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         // ======================================================= NF4 decode ====
         // NG groups of BNC threads; group g takes ring positions it with it % NG == g.  One thread
         // = one quantisation block (64 weights, one absmax, one 128-byte operand row) per stage.
-        const int g = (threadIdx.x - 256) / Cfg::NDT;
-        const int t = (threadIdx.x - 256) % Cfg::NDT;
+        // Decode warps are the warp ids {0, 2, 3, 8, 10, 11, 12, 14} (see the role map in GemmCfg); 15 is idle.
+        const int wi = warp < 4 ? (warp == 0 ? 0 : warp - 1) : 3 + (warp - 8) - ((warp - 6) >> 2);   // index among them
+        if (wi >= NG * Cfg::NDW) goto decode_done;
+        {
+        const int g = wi / Cfg::NDW;
+        const int t = (wi % Cfg::NDW) * 32 + lane;
         float code16[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) code16[i] = __ldg(p.code16 + i);
@@ -726,6 +744,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             it += kb_total;
             pit += p.kb_main;
         }
+        }
+        decode_done:;
       }
     }
 
@@ -733,7 +753,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     __syncwarp();  // single-lane roles (producer, UMMA issuer) rejoin their warp before the aligned barrier
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync(); else __syncthreads();
-    if (warp == 2) {
+    if (warp == Cfg::W_ALLOC) {
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
     }
