@@ -88,7 +88,8 @@ struct GemmCfg {
     static constexpr bool EPI_COAL = STG_ < 0;
     static constexpr int STG_BYTES = STG_ != 0 ? 4 * 4096 : 0;
     static constexpr bool A_XF = A_XF_;           // dropout mask applied to the A tile in shared memory
-    static constexpr int XF_THREADS = A_XF_ ? 256 : 0;
+    static constexpr int XF_GROUPS = 4;                 // transform groups of 128 threads taking ring positions in turn
+    static constexpr int XF_THREADS = A_XF_ ? 128 * XF_GROUPS : 0;
     static constexpr int NG = B_DEC_ ? NG_ : 0;   // decode groups (each BNC threads)
     static constexpr int PST = B_DEC_ ? PST_ : 0; // packed-NF4 ring depth
     static constexpr int CG = CG_;          // CTAs per MMA (cta_group)
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             mbar_init(empty_bar(s), 1);                   // tcgen05.commit
         }
         if constexpr (Cfg::A_XF)
-            for (int s = 0; s < STAGES; ++s) mbar_init(xf_bar(s), Cfg::XF_THREADS / 64);  // one arrive per warp of the owning group
+            for (int s = 0; s < STAGES; ++s) mbar_init(xf_bar(s), 4);  // one arrive per warp of the owning 128-thread group
         for (int s = 0; s < PST; ++s) {
             mbar_init(pk_bar(s), 1);                      // packed-ring producer (+tx)
             mbar_init(pk_empty_bar(s), Cfg::NDW);         // decode warps, once the bytes are in registers
@@ -604,11 +605,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
       if constexpr (Cfg::A_XF) {
         // ============================================ A-operand transform ====
         // LoRA dropout: zero the dropped elements of the A tile in place (the 1/(1-p) scale is folded
-        // into the epilogue).  Two groups of 128 threads take ring positions alternately, so two stages are
+        // into the epilogue).  XF_GROUPS groups of 128 threads take ring positions in turn, so several stages are
         // being transformed at any time (one group alone is latency-bound: barrier wake-up, LDS, hash, STS,
         // proxy fence, arrive per stage).  A thread handles eight 16-byte chunks (8 bf16 each) of its stage;
         // chunk q sits at byte q*16: row q>>3, physical chunk q&7 holds logical chunk (q&7)^(row&7).
-        constexpr int XG = 2, XT = Cfg::XF_THREADS / XG;
+        constexpr int XG = Cfg::XF_GROUPS, XT = Cfg::XF_THREADS / XG;
         const int g = (threadIdx.x - 256) / XT;
         const int t = (threadIdx.x - 256) % XT;
         const uint32_t seed_lo = static_cast<uint32_t>(p.seed), seed_hi = static_cast<uint32_t>(p.seed >> 32);
