@@ -243,8 +243,8 @@ template <int R> constexpr int skinny_stages() { return 6; }
 template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>()>;   // u = x A^T
 template <int R> using DownDropCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>(), 0, 0, true>;   // u = drop(x) A^T
 template <int R> using GradADropCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true>;
-// dx += keep * (du A) / (1 - p): masked epilogue, TMA reduce-add into dx (dropout backward)
-using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 5, 0, 0, false, 1>;
+// dx += keep * (du A) / (1 - p): masked epilogue, 128-bit vector reductions into dx at the L2 (dropout backward)
+using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 5, 0, 0, false, -1>;
 template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, skinny_stages<R>()>;      // du = s dy B
 template <int R> using GradACfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6>;  // dA^T tile, stored transposed
 template <int R> using GradBCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART, 6>;    // dB tile
@@ -374,7 +374,7 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
         default: if ((e = setup(DxV5::BNC, slab(DxV5::TILE_M)))) return e; e = launch<DxV5>(p, stream); break;
     }
     if (e || !masked) return e;
-    // LoRA dropout: dx += keep * (du @ A) / (1 - p) -- masked epilogue, reduce-added into dx by the copy engine
+    // LoRA dropout: dx += keep * (du @ A) / (1 - p) -- masked epilogue, reduce-added into dx at the L2
     GemmParams q;
     memset(&q, 0, sizeof(q));
     q.D = dx; q.ldd = K; q.alpha = 1.0f / (1.0f - drop_p); q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
@@ -382,7 +382,6 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
     q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.xf_ld = K;
     if ((e = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return e;
     if ((e = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return e;
-    if ((e = map_bf16_out(&q.tmD, dx, M, K, K))) return e;
     return launch<GemmKNMask>(q, stream);
 }
 

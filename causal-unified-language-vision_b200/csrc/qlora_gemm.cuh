@@ -486,32 +486,23 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         }
                         __nv_bfloat16* gp = Dp + static_cast<long long>(row_w) * ldd_r + (n0 + c * 64 + ch * 8);
                         if (accum_r) {
-                            uint4 old[8];
+                            // D += tile: 128-bit vector reductions performed at the L2 (fire and forget, no read into
+                            // the SM); bf16 add with round-to-nearest, i.e. D = bf16(D + bf16(alpha * acc))
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                old[i] = make_uint4(0u, 0u, 0u, 0u);
-                                if (row_w + i * 4 < M_r) old[i] = *reinterpret_cast<const uint4*>(gp + static_cast<long long>(i) * 4 * ldd_r);
+                                const uint32_t ok = (row_w + i * 4 < M_r) ? 1u : 0u;
+                                asm volatile("{\n\t.reg .pred P1;\n\tsetp.ne.b32 P1, %5, 0;\n\t@P1 red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};\n\t}\n"
+                                             ::"l"(gp + static_cast<long long>(i) * 4 * ldd_r), "r"(val[i].x), "r"(val[i].y),
+                                               "r"(val[i].z), "r"(val[i].w), "r"(ok) : "memory");
                             }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const uint32_t a[4] = {old[i].x, old[i].y, old[i].z, old[i].w};
-                                uint32_t b[4] = {val[i].x, val[i].y, val[i].z, val[i].w};
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&a[t]);
-                                    const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&b[t]);
-                                    b[t] = pack_bf16x2(__bfloat162float(x2.x) + __bfloat162float(y2.x),
-                                                       __bfloat162float(x2.y) + __bfloat162float(y2.y));
-                                }
-                                val[i] = make_uint4(b[0], b[1], b[2], b[3]);
-                            }
-                        }
+                        } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const uint32_t ok = (row_w + i * 4 < M_r) ? 1u : 0u;
                             asm volatile("{\n\t.reg .pred P1;\n\tsetp.ne.b32 P1, %5, 0;\n\t@P1 st.global.v4.b32 [%0], {%1,%2,%3,%4};\n\t}\n"
                                          ::"l"(gp + static_cast<long long>(i) * 4 * ldd_r), "r"(val[i].x), "r"(val[i].y),
                                            "r"(val[i].z), "r"(val[i].w), "r"(ok) : "memory");
+                        }
                         }
                     }
                 }
