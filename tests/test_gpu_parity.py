@@ -388,3 +388,38 @@ def test_gemv_single_token_path(F, cuda_dev, M, N, K, dq):
             out = lin(x.to(cuda_dev))
         assert F.launch_count() - launches == 1 and out.shape == (M, N)
         assert rel_err(out.cpu(), F.qlora_fwd(x.to(cuda_dev), lin.weight.data, lin.weight.quant_state, None, None).cpu()) <= 1e-2
+
+
+@pytest.mark.parametrize("N,K", [(14336, 4096), (4096, 14336)])
+def test_full_size_mlp_projections_against_cublas_with_dropout(F, cuda_dev, N, K):
+    """BASELINE's largest projections at M = 4096 (too large for the CPU oracle to finish in seconds): every output
+    of the fused path against stock torch ops on the GPU using the materialised (bit-exact) bf16 weight and the
+    dropout mask exported from the kernels' own generator."""
+    M, r, s, p, seed = 4096, 64, 0.25, 0.05, 4242
+    g = torch.Generator(device=cuda_dev).manual_seed(N)
+    packed, qs = F.quantize_4bit(torch.empty(N, K, device=cuda_dev).normal_(0, 0.02, generator=g), compress_statistics=True)
+    x = torch.empty(M, K, device=cuda_dev).normal_(generator=g).bfloat16()
+    dy = (torch.empty(M, N, device=cuda_dev).normal_(generator=g) / N ** 0.5).bfloat16()
+    A = ((torch.rand(r, K, device=cuda_dev, generator=g) * 2 - 1) / K ** 0.5).bfloat16()
+    B = torch.empty(N, r, device=cuda_dev).normal_(0, 0.02, generator=g).bfloat16()
+    # fused path
+    u, us = F.lora_down(x, A, s, seed, p)
+    y = F.qlora_fwd(x, packed, qs, us, B)
+    du = F.lora_bwd_du(dy, B, s)
+    dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)
+    dA, dB = torch.zeros_like(A), torch.zeros_like(B)
+    F.lora_grads(dy, x, u, du, s, dA, dB, seed=seed, p=p)
+    # stock-torch statement of the same math (fp32 where the reference accumulates in fp32)
+    W = F.dequantize_4bit(packed, qs)
+    mask = F.dropout_mask((M, K), seed, p, cuda_dev).to(torch.bfloat16)
+    xd = (x.float() * mask.float() / (1 - p)).bfloat16()
+    u_ref = (xd @ A.t())
+    y_ref = (x @ W.t()).float() + (u_ref @ B.t()).float() * s
+    du_ref = ((dy.float() * s).bfloat16() @ B)
+    dx_ref = (dy @ W).float() + (du_ref @ A).float() * mask.float() / (1 - p)
+    dA_ref = du_ref.float().t() @ xd.float()
+    dB_ref = (dy.float() * s).t() @ u_ref.float()
+    rel = lambda a, b: float((a.float() - b.float()).abs().max() / b.float().abs().max())
+    for name, got, ref in (("u", u, u_ref), ("y", y, y_ref), ("du", du, du_ref), ("dx", dx, dx_ref), ("dA", dA, dA_ref),
+                           ("dB", dB, dB_ref)):
+        assert rel(got, ref) <= TOL, (name, rel(got, ref))
