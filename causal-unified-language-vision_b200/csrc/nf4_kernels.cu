@@ -6,6 +6,8 @@
 // Replaces (reference side, third-party):
 //   cdequantize_blockwise_bf16_nf4 (+ nested cdequantize_blockwise_fp32)  -> b2q_nf4_decode
 //   cquantize_blockwise_*_nf4 (+ cquantize_blockwise_fp32 for the absmax) -> b2q_nf4_quantize
+#include <cstdlib>
+
 #include "b2q_decode.cuh"
 #include "b2q_internal.h"
 
@@ -54,12 +56,12 @@ __global__ void __launch_bounds__(256) nf4_decode_kernel(const uint32_t* __restr
 // 16 packed bytes (half a quantisation block, one absmax) per step with 128-bit loads, decodes them with the same
 // pre-scaled LUT as the GEMM main loops (bit-identical bf16 weights), accumulates in fp32 and the warp reduces with
 // shuffles.  Replaces bitsandbytes `cgemm_4bit_inference_naive_bf16` (kgemm_4bit_inference_naive).
-template <int MROWS>
-__global__ void __launch_bounds__(128) nf4_gemv_kernel(const __nv_bfloat16* __restrict__ x, const uint4* __restrict__ packed,
+template <int MROWS, int RPW, int U, int MINB>
+__global__ void __launch_bounds__(128, MINB) nf4_gemv_kernel(const __nv_bfloat16* __restrict__ x, const uint4* __restrict__ packed,
                                                        AbsmaxSrc am, const float* __restrict__ code16_g,
                                                        __nv_bfloat16* __restrict__ y, int M, int N, int K) {
-    constexpr int RPW = 2;   // output rows per warp: every x chunk fetched from L1 is used for both
-    constexpr int U = 2;     // chunks in flight per lane and row (memory-level parallelism)
+    // RPW: output rows per warp (every x chunk fetched from L1 is used for all of them); U: chunks in flight per lane
+    // and row (memory-level parallelism); MINB: resident blocks per SM the register allocation must allow
     float code16[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) code16[i] = __ldg(code16_g + i);
@@ -355,13 +357,21 @@ extern "C" int b2q_gemv_4bit(const void* x_bf16, const b2q_nf4_weight* w, void* 
     if (M < 0 || M > 8 || K % 64 != 0 || N <= 0) return B2Q_ERR_SHAPE;
     if (((reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(w->packed)) & 15) != 0) return B2Q_ERR_ARG;
     AbsmaxSrc am{w->absmax, w->absmax_q, w->absmax2, w->code256, w->offset};
-    const int grid = (N + 7) / 8;   // 4 warps x 2 rows per block
+    static int cfg = -1;   // tuning hook: B2Q_GEMV_CFG = 0 (2 rows/warp, 2 in flight), 1 (1 row, 4 in flight, 8 blocks/SM), 2 (2 rows, 2, 6 blocks/SM)
+    if (cfg < 0) { const char* e = getenv("B2Q_GEMV_CFG"); cfg = e ? atoi(e) : 1; }
     const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
     const uint4* pk = reinterpret_cast<const uint4*>(w->packed);
-    if (M == 1) nf4_gemv_kernel<1><<<grid, 128, 0, stream>>>(x, pk, am, w->code16, y, M, N, K);
-    else if (M <= 4) nf4_gemv_kernel<4><<<grid, 128, 0, stream>>>(x, pk, am, w->code16, y, M, N, K);
-    else nf4_gemv_kernel<8><<<grid, 128, 0, stream>>>(x, pk, am, w->code16, y, M, N, K);
+#define B2Q_GEMV_LAUNCH(MR, RPW_, U_, MINB_) \
+    nf4_gemv_kernel<MR, RPW_, U_, MINB_><<<(N + 4 * RPW_ - 1) / (4 * RPW_), 128, 0, stream>>>(x, pk, am, w->code16, y, M, N, K)
+    if (M == 1) {
+        if (cfg == 0) B2Q_GEMV_LAUNCH(1, 2, 2, 1); else if (cfg == 2) B2Q_GEMV_LAUNCH(1, 2, 2, 6); else B2Q_GEMV_LAUNCH(1, 1, 4, 8);
+    } else if (M <= 4) {
+        if (cfg == 0) B2Q_GEMV_LAUNCH(4, 2, 2, 1); else B2Q_GEMV_LAUNCH(4, 2, 2, 4);
+    } else {
+        if (cfg == 0) B2Q_GEMV_LAUNCH(8, 2, 2, 1); else B2Q_GEMV_LAUNCH(8, 2, 2, 4);
+    }
+#undef B2Q_GEMV_LAUNCH
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
