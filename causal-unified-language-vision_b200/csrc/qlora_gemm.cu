@@ -244,7 +244,7 @@ template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16,
 template <int R> using DownDropCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>(), 0, 0, true>;   // u = drop(x) A^T
 template <int R> using GradADropCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true>;
 // dx += keep * (du A) / (1 - p): masked epilogue, 128-bit vector reductions into dx at the L2 (dropout backward)
-using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 5, 0, 0, false, -1>;
+using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 5, 0, 0, false, -1, 2>;   // two epilogue warp sets
 template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, skinny_stages<R>()>;      // du = s dy B
 template <int R> using GradACfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6>;  // dA^T tile, stored transposed
 template <int R> using GradBCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART, 6>;    // dB tile

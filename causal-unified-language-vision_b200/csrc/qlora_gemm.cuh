@@ -75,8 +75,11 @@ struct GemmParams {
 };
 
 template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_, int NG_ = 2,
-          int PST_ = 6, bool A_XF_ = false, int STG_ = 0>
+          int PST_ = 6, bool A_XF_ = false, int STG_ = 0, int ESETS_ = 1>
 struct GemmCfg {
+    // ESETS = 2: two sets of four epilogue warps (4-7 and 8-11), one per accumulator stage, for kernels that are all
+    // epilogue (one k-block per tile): set e drains the tiles whose sequence number is e (mod 2).
+    static constexpr int ESETS = ESETS_;
     // STG > 0: the bf16 epilogue goes TMEM -> registers -> swizzled shared-memory staging (32 rows x 64
     // columns per epilogue warp) -> TMA store (or TMA reduce-add when accum_d), so global memory sees whole
     // 128-byte row segments written by the copy engine instead of 32 scattered 16-byte stores per warp
@@ -86,7 +89,7 @@ struct GemmCfg {
     // instruction (or read-modify-write when accum_d).
     static constexpr bool EPI_TMA = STG_ > 0;
     static constexpr bool EPI_COAL = STG_ < 0;
-    static constexpr int STG_BYTES = STG_ != 0 ? 4 * 4096 : 0;
+    static constexpr int STG_BYTES = STG_ != 0 ? ESETS_ * 4 * 4096 : 0;
     static constexpr bool A_XF = A_XF_;           // dropout mask applied to the A tile in shared memory
     static constexpr int XF_GROUPS = 4;                 // transform groups of 128 threads taking ring positions in turn
     static constexpr int XF_THREADS = A_XF_ ? 128 * XF_GROUPS : 0;
@@ -124,7 +127,8 @@ struct GemmCfg {
     static constexpr int W_MMA = 1;
     static constexpr int W_ALLOC = B_DEC ? 13 : 2;
     static constexpr int W_PACK = B_DEC ? 13 : -1;
-    static constexpr int THREADS = 256 + NG * NDT + XF_THREADS;
+    static constexpr int THREADS = 256 + NG * NDT + XF_THREADS + (ESETS_ - 1) * 128;
+    static_assert(ESETS_ == 1 || (ESETS_ == 2 && !B_DEC_ && !A_XF_ && 2 * MT_ * BN_ <= 512), "two epilogue sets: double-buffered accumulator, no decode / transform warps");
     static_assert(!B_DEC || NG * NDT == 256, "decode role map assumes 8 decode warps");
     static_assert(!(A_XF_ && B_DEC_), "A transform and B decode share the warps 8+");
     static_assert(!A_XF_ || (MT_ == 1 && CG_ == 1), "A transform: single 128-row tile, single CTA");
@@ -379,14 +383,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 4 + 4 * Cfg::ESETS) {
         // ========================================================= epilogue ====
         const int wq = warp & 3;  // TMEM lane quadrant this warp may access
-        int as = 0;
+        const int eset = (warp - 4) >> 2;   // epilogue set (0 unless ESETS == 2)
+        int as = Cfg::ESETS == 2 ? eset : 0;
         uint32_t aph = 0;
         [[maybe_unused]] const uint32_t stg_base = smem_base + Cfg::RING_BYTES + Cfg::BAR_BYTES + Cfg::CODE256_BYTES;
-        int tseq = 0;
-        for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tseq) {
+        int tseq = Cfg::ESETS == 2 ? eset : 0;
+        for (int tile = pair_id + (Cfg::ESETS == 2 ? eset * num_pairs : 0); tile < num_tiles; tile += Cfg::ESETS * num_pairs, tseq += Cfg::ESETS) {
             int mt_i, nt_i, split;
             tile_coords(p, tile, mt_i, nt_i, split);
             const int m0 = mt_i * p.tile_m;
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 // warp reads it back 4 rows x 128 B per instruction and writes global memory itself (EPI_COAL).
                 constexpr int GPM = BN / 64, NG64 = MT * GPM;
                 const uint32_t t_warp = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * ACC_COLS;
-                const uint32_t stg = stg_base + wq * 4096;
+                const uint32_t stg = stg_base + (eset * 4 + wq) * 4096;
                 const float alpha_r = p.alpha;
                 const bool unit = alpha_r == 1.0f;
                 __nv_bfloat16* Dp = reinterpret_cast<__nv_bfloat16*>(p.D);
@@ -587,7 +592,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 }
             }
             if (tr != nullptr) tr[6] = clock64();
-            if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
+            if constexpr (Cfg::ESETS == 2) { aph ^= 1u; } else { if (++as == ACC_STAGES) { as = 0; aph ^= 1u; } }
         }
         if constexpr (Cfg::EPI_TMA) {
             if (lane == 0) tma_store_wait<0>();   // all bulk stores of this warp are complete before the CTA exits
