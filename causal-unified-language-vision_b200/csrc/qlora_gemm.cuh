@@ -620,18 +620,21 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 const int k0 = (kb0 + kb) * 64;
                 const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
                 mbar_wait(full_bar(s), ph);
+                // hash counter of chunk i = counter of chunk 0 + a multiple of xf_ld (XT = 128: rows advance by 16 per chunk)
+                uint32_t j0_base;
+                {
+                    const int r0 = t >> 3, cl = (t & 7) ^ (r0 & 7);
+                    const long long e_base = Cfg::A_MN ? static_cast<long long>(k0 + r0) * p.xf_ld + row0 + cl * 8
+                                                       : static_cast<long long>(row0 + r0) * p.xf_ld + k0 + cl * 8;
+                    j0_base = static_cast<uint32_t>(static_cast<unsigned long long>(e_base) >> 2);
+                }
+                const uint32_t j0_step = static_cast<uint32_t>(p.xf_ld) * 4u;   // 16 rows further = 16 * xf_ld elements = 4 * xf_ld counters
 #pragma unroll
                 for (int i = 0; i < 1024 / XT; ++i) {
                     const int q = t + XT * i;
-                    const int rr = (q >> 3) & 63, cl = (q & 7) ^ (rr & 7);
-                    long long e0;
-                    if constexpr (!Cfg::A_MN) {   // rows = MN coordinate, 64 contraction elements per row
-                        const int row = q >> 3;
-                        e0 = static_cast<long long>(row0 + row) * p.xf_ld + k0 + ((q & 7) ^ (row & 7)) * 8;
-                    } else {                      // rows = contraction coordinate, two boxes of 64 MN elements
-                        e0 = static_cast<long long>(k0 + rr) * p.xf_ld + row0 + (q >> 9) * 64 + cl * 8;
-                    }
-                    const uint32_t j0 = static_cast<uint32_t>(static_cast<unsigned long long>(e0) >> 2);
+                    static_assert(XT == 128, "chunk -> row mapping below assumes 128 threads per transform group");
+                    const uint32_t j0 = Cfg::A_MN ? j0_base + static_cast<uint32_t>(i & 3) * j0_step + static_cast<uint32_t>(i >> 2) * 16u
+                                                  : j0_base + static_cast<uint32_t>(i) * j0_step;
                     const uint32_t addr = a_stage(s) + q * 16;
                     uint32_t w[4];
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
