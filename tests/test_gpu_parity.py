@@ -158,22 +158,24 @@ def test_base_only_and_lora_b_zero(F, cuda_dev):
     assert float(dA.float().abs().max()) == 0.0
 
 
-def test_dropout_path_against_oracle(F, cuda_dev):
-    """p = 0.05 with the kernel's own counter-based mask exported to the oracle."""
+@pytest.mark.parametrize("M,r", [(512, 64), (200, 64), (333, 128)])
+def test_dropout_path_against_oracle(F, cuda_dev, M, r):
+    """p = 0.05 with the kernel's own counter-based mask exported to the oracle (ragged M and r = 128 included)."""
     from oracle.qlora import make_case, qlora_linear_fwd_bwd, rel_err
 
     auto = importlib.import_module("causal-unified-language-vision_b200.autograd")
-    M, N, K, r, p, seed = 512, 512, 768, 64, 0.05, 1234
+    N, K, p, seed = 512, 768, 0.05, 1234
     case = make_case(M, N, K, r, seed=21)
     mask = F.dropout_mask((M, K), seed, p, cuda_dev)
     keep = float(mask.float().mean())
     assert abs(keep - (1 - p)) < 0.01
-    ref = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], 0.25, case["dy"], mask.cpu(), p, "bf16")
+    s = 16.0 / r
+    ref = qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], s, case["dy"], mask.cpu(), p, "bf16")
     packed, qs = _state_to_gpu(case["state"], cuda_dev)
     x = case["x"].to(cuda_dev).requires_grad_(True)
     A = case["A"].to(cuda_dev).requires_grad_(True)
     B = case["B"].to(cuda_dev).requires_grad_(True)
-    y = auto.qlora_linear(x, packed, qs, A, B, 0.25, p, seed, None)
+    y = auto.qlora_linear(x, packed, qs, A, B, s, p, seed, None)
     y.backward(case["dy"].to(cuda_dev))
     for name, got in (("y", y), ("dx", x.grad), ("dA", A.grad), ("dB", B.grad)):
         assert rel_err(got.detach().cpu(), ref[name]) <= TOL, name
