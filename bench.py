@@ -172,6 +172,7 @@ def main():
     import torch.distributed as dist
     from importlib import import_module
 
+    t_start = time.perf_counter()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference "
                          "for the CPU oracle)")
@@ -179,7 +180,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # fail fast instead of hanging the box if a rank gets stuck
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     import b200qlora as q
 
     stackmod = import_module("causal-unified-language-vision_b200.stack")
@@ -194,6 +198,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def mark(what):  # progress markers on stderr (one line per rank and phase): tells where a rank stopped if a run hangs
+        print(f"[bench rank {rank}] {what} t={time.perf_counter() - t_start:.1f}s", file=sys.stderr, flush=True)
+
+    mark("stack built")
 
     # ---- per-launch timing of the dominant kernel (events on the launching stream) -------------
     main_events, main_flops = [], [0.0]
@@ -228,6 +237,7 @@ def main():
     for _ in range(args.warmup):
         stack.step_direct(recompute=args.recompute)
     barrier()
+    mark("value warm-up done")
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = F.launch_count()
@@ -241,6 +251,7 @@ def main():
     timing_on[0] = False
     launches = F.launch_count() - launches0
     clocks = sampler.stop()
+    mark("value timed steps done")
     ms = t0.elapsed_time(t1) / args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -282,8 +293,10 @@ def main():
             torch.cuda.current_stream().synchronize()
             return float(host_out[0])
 
-        for _ in range(2):
+        mark("e2e host buffers pinned")
+        for i in range(2):
             e2e_step()
+            mark(f"e2e warm-up step {i} done")
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -292,6 +305,7 @@ def main():
         e1.record()
         barrier()
         ems = e0.elapsed_time(e1) / args.steps
+        mark("e2e timed steps done")
         if world > 1:
             t = torch.tensor([ems], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

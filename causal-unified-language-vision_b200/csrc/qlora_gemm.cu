@@ -157,7 +157,7 @@ static GradPlan grad_plan(int rows, int kblocks) {
 static long long* g_trace = nullptr;   // debug: phase trace buffer for the next launches (b2q_debug_set_trace)
 static int g_trace_tiles = 0;
 static int g_pf_dist = 0;
-static int g_pdl = -1;   // -1: read B2Q_PDL (default on)
+static int g_pdl = -1;   // -1: read B2Q_PDL (default off)
 
 template <class Cfg>
 static int launch(GemmParams& p, cudaStream_t stream) {
@@ -168,7 +168,7 @@ static int launch(GemmParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return static_cast<int>(e);
         attr_set = true;
     }
-    if (g_pdl < 0) { const char* v = getenv("B2Q_PDL"); g_pdl = v ? atoi(v) : 1; }
+    if (g_pdl < 0) { const char* v = getenv("B2Q_PDL"); g_pdl = v ? atoi(v) : 0; }   // opt-in: no measurable gain
     p.trace = g_trace;
     p.trace_tiles = g_trace_tiles;
     p.pf_dist = g_pf_dist;
