@@ -54,9 +54,18 @@ class _Bucket:
 
 class GradSync:
     def __init__(self, modules: Sequence, adapter_name: str, process_group=None, bucket_bytes: int = 64 << 20,
-                 grad_dtype: torch.dtype = torch.bfloat16, install: bool = True):
+                 grad_dtype: torch.dtype = torch.bfloat16, install: bool = True, overlap: Optional[bool] = None):
         """``modules``: the LoRA-wrapped linears in FORWARD order (``LoraLinear4bit`` or anything with
         ``lora_A[adapter].weight`` / ``lora_B[adapter].weight``)."""
+        # overlap=True: a bucket's all-reduce is issued on a side stream as soon as its last gradient kernel is enqueued
+        # and runs concurrently with the rest of backward.  overlap=False (default, B2Q_GRAD_OVERLAP=1 flips it): all
+        # buckets are reduced on the compute stream at finish().  The exchange is 360 MB per 460 ms step (< 1 ms on
+        # NVLink), so serialising it costs ~0.2 %; running NCCL's kernels concurrently with the persistent, all-SM
+        # tcgen05 kernels hung intermittently at 4 GPUs (DESIGN.md, open issue), so the safe order is the default.
+        if overlap is None:
+            import os
+            overlap = os.environ.get("B2Q_GRAD_OVERLAP", "0") == "1"
+        self.overlap = bool(overlap)
         self.adapter = adapter_name
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -116,6 +125,7 @@ class GradSync:
     def begin_step(self) -> None:
         """Call after ``zero_grad`` / before the first backward of an optimizer step."""
         self._written.clear()
+        self._reduced = False
         for b in self.buckets:
             b.pending = len(b.members)
             b.work = None
@@ -137,13 +147,15 @@ class GradSync:
             bi = self._slot_bucket[(key, which)]
             b = self.buckets[bi]
             b.pending -= 1
-            if b.pending == 0 and self.world > 1 and not self.defer:
+            if b.pending == 0 and self.world > 1 and not self.defer and self.overlap:
                 self._launch(b)
 
     defer = False  # True while accumulating micro-batches: reduce only on the last one
 
     def _launch(self, b: _Bucket) -> None:
-        if self._use_cuda:
+        if self._use_cuda and not self.overlap:
+            dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.group)   # on the compute stream, in order
+        elif self._use_cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             self.comm_stream.wait_event(ev)
@@ -161,9 +173,14 @@ class GradSync:
         if self.world > 1:
             for b in self.buckets:
                 self._launch(b)
+            self._reduced = True
 
     def finish(self) -> None:
-        """Order the optimizer step after every in-flight all-reduce."""
+        """Order the optimizer step after every all-reduce (issuing them here when not overlapping)."""
+        if self.world > 1 and not self.overlap and not self.defer and not self._reduced:
+            for b in self.buckets:
+                self._launch(b)
+            self._reduced = True
         if self._use_cuda:
             cur = torch.cuda.current_stream(self.device)
             for ev in self._done_events:
