@@ -29,21 +29,23 @@ def _flatten(x: torch.Tensor):
 class MatMul4Bit(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, packed, qs):
-        x2, lead = _flatten(x)
-        ctx.qs = qs
-        ctx.lead = lead
-        ctx.in_dtype = x.dtype
-        ctx.save_for_backward(packed)
-        y = F.qlora_fwd(x2, packed, qs, None, None)
-        return y.reshape(*lead, y.shape[-1])
+        with torch.cuda.device(x.device):   # bitsandbytes' pre_call(A.device): the C ABI launches on the current device
+            x2, lead = _flatten(x)
+            ctx.qs = qs
+            ctx.lead = lead
+            ctx.in_dtype = x.dtype
+            ctx.save_for_backward(packed)
+            y = F.qlora_fwd(x2, packed, qs, None, None)
+            return y.reshape(*lead, y.shape[-1])
 
     @staticmethod
     def backward(ctx, dy):
         (packed,) = ctx.saved_tensors
         dx = None
         if ctx.needs_input_grad[0]:
-            dy2, _ = _flatten(dy)
-            dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, None, None).reshape(*ctx.lead, -1).to(ctx.in_dtype)
+            with torch.cuda.device(dy.device):   # backward may run on an autograd engine thread
+                dy2, _ = _flatten(dy)
+                dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, None, None).reshape(*ctx.lead, -1).to(ctx.in_dtype)
         return dx, None, None
 
 
@@ -73,6 +75,11 @@ class QLoRALinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, packed, qs, A, B, scale, p, seed, grad_sink):
+        with torch.cuda.device(x.device):   # the C ABI launches on the current device of the calling thread
+            return QLoRALinear._forward(ctx, x, packed, qs, A, B, scale, p, seed, grad_sink)
+
+    @staticmethod
+    def _forward(ctx, x, packed, qs, A, B, scale, p, seed, grad_sink):
         x2, lead = _flatten(x)
         a = A if A.dtype == torch.bfloat16 else A.to(torch.bfloat16)
         b = B if B.dtype == torch.bfloat16 else B.to(torch.bfloat16)
@@ -88,6 +95,11 @@ class QLoRALinear(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        with torch.cuda.device(dy.device):   # backward usually runs on an autograd engine thread
+            return QLoRALinear._backward(ctx, dy)
+
+    @staticmethod
+    def _backward(ctx, dy):
         x2, packed, a, b, u = ctx.saved_tensors
         dy2, _ = _flatten(dy)
         need_x, need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[3], ctx.needs_input_grad[4]

@@ -131,7 +131,7 @@ class QLoRALinearStack(nn.Module):
         self.sync.finish()
         self._step += 1
 
-    def step_modules(self, inputs: Optional[dict] = None, grads_out: Optional[dict] = None) -> torch.Tensor:
+    def step_modules(self, inputs: Optional[dict] = None, grads_out: Optional[dict] = None, trace=None) -> torch.Tensor:
         """Same work through ``LoraLinear4bit.forward`` + autograd.  Returns the squared gradient norm (device scalar)."""
         inputs = self.inputs if inputs is None else inputs
         grads_out = self.grads_out if grads_out is None else grads_out
@@ -140,11 +140,17 @@ class QLoRALinearStack(nn.Module):
         for mod in self.mods:
             x = inputs[mod.in_features].detach().requires_grad_(True)
             outs.append((mod(x), x))
+        if trace is not None:
+            trace("forward done")
         for i in range(len(self.mods) - 1, -1, -1):
             y, x = outs[i]
             torch.autograd.backward(y, grads_out[y.shape[-1]])
             outs[i] = None
+            if trace is not None and i % 56 == 0:
+                trace(f"backward down to module {i} done")
         self.sync.finish()
+        if trace is not None:
+            trace("grad sync done")
         self._step += 1
         total = None
         for flat in self.sync.flat_grads():
