@@ -348,7 +348,7 @@ def main():
             ins = {k: widen(x, k) for k in widths_in}
             gos = {n: widen(dy, n) for n in widths_out}
             tmark("widen done")
-            g2 = stack.step_modules(ins, gos, tmark if trace else None)
+            g2 = stack.step_modules(ins, gos, tmark if trace else None, interleaved=(world > 1))
             tmark("step_modules done")
             host_out.copy_(g2.reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -372,7 +372,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         e2e = {"value": M * world / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": ems, "api": "LoraLinear4bit.forward + autograd (QLoRALinear) -> C ABI"}
+               "ms_per_step": ems, "api": "LoraLinear4bit.forward + autograd (QLoRALinear) -> C ABI",
+               "order": "per-module forward+backward, single-threaded autograd (n_gpus > 1)" if world > 1
+                        else "forward of all modules, then backward of all"}
 
     # ---- the step either side of the path: fused clip + AdamW on the flat buckets (reported, not part of `value`) ---
     opt_info = None

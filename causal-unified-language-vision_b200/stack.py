@@ -131,11 +131,30 @@ class QLoRALinearStack(nn.Module):
         self.sync.finish()
         self._step += 1
 
-    def step_modules(self, inputs: Optional[dict] = None, grads_out: Optional[dict] = None, trace=None) -> torch.Tensor:
+    def step_modules(self, inputs: Optional[dict] = None, grads_out: Optional[dict] = None, trace=None,
+                     interleaved: bool = False) -> torch.Tensor:
         """Same work through ``LoraLinear4bit.forward`` + autograd.  Returns the squared gradient norm (device scalar)."""
         inputs = self.inputs if inputs is None else inputs
         grads_out = self.grads_out if grads_out is None else grads_out
         self.sync.begin_step()
+        if interleaved:
+            # memory-lean order (forward + backward per module, last module first): same kernels and launch count as
+            # the all-forward / all-backward order, but no 50 GB of live outputs
+            for i in range(len(self.mods) - 1, -1, -1):
+                mod = self.mods[i]
+                x = inputs[mod.in_features].detach().requires_grad_(True)
+                y = mod(x)
+                torch.autograd.backward(y, grads_out[y.shape[-1]])
+                del y, x
+                if trace is not None and i % 56 == 0:
+                    trace(f"fwd+bwd down to module {i} done")
+            self.sync.finish()
+            self._step += 1
+            total = None
+            for flat in self.sync.flat_grads():
+                v = flat.float().pow(2).sum()
+                total = v if total is None else total + v
+            return total
         outs = []
         for mod in self.mods:
             x = inputs[mod.in_features].detach().requires_grad_(True)
