@@ -1,4 +1,4 @@
-"""Data-parallel LoRA-gradient sync: flat buckets + NCCL all-reduce(mean) overlapped with backward.
+"""Data-parallel LoRA-gradient sync: flat buckets + NCCL all-reduce(mean), optionally overlapped with backward.
 
 What it replaces: the DDP reducer that ``accel.prepare`` installs
 (/root/reference/trainer/utils_trainer.py:32-37) and ``accel.backward`` is meant to drive
@@ -13,10 +13,12 @@ Design (one process per GPU, weights replicated, batch sharded):
     REVERSE forward order (the order backward produces them); ``param.grad`` is that view;
   * the backward kernels (``b2q_lora_grads``) write dA / dB straight into the views -- no
     autograd accumulation pass, no flatten / unflatten copies;
-  * when the last gradient of a bucket has been produced an event is recorded on the compute
-    stream, the comm stream waits on it and issues ONE ``all_reduce`` for the bucket
-    (NCCL over NVLink 5 / NVSwitch; ``ReduceOp.AVG``), overlapping the remaining backward;
-  * ``finish()`` makes the compute stream wait for the comm stream before the optimizer step.
+  * ``overlap=True``: when the last gradient of a bucket has been produced an event is recorded on the
+    compute stream, the comm stream waits on it and issues ONE ``all_reduce`` for the bucket
+    (NCCL over NVLink 5 / NVSwitch; ``ReduceOp.AVG``), overlapping the remaining backward, and
+    ``finish()`` makes the compute stream wait for the comm stream before the optimizer step;
+  * ``overlap=False`` (default since the end of round 1, see DESIGN.md "open issue"): ``finish()`` issues
+    the all-reduces of all buckets on the compute stream -- 360 MB per step, < 1 ms on NVLink.
 The same class runs on CPU tensors with the ``gloo`` backend (SUM then divide) for tests.
 """
 from __future__ import annotations
