@@ -425,3 +425,12 @@ def test_full_size_mlp_projections_against_cublas_with_dropout(F, cuda_dev, N, K
     for name, got, ref in (("u", u, u_ref), ("y", y, y_ref), ("du", du, du_ref), ("dx", dx, dx_ref), ("dA", dA, dA_ref),
                            ("dB", dB, dB_ref)):
         assert rel(got, ref) <= TOL, (name, rel(got, ref))
+
+
+def test_dropout_mask_matches_cpu_restatement(F, cuda_dev):
+    """The mask the kernels use (exported by b2q_dropout_mask) equals the independent numpy restatement bit for bit."""
+    from oracle import dropout
+
+    for shape, seed, p in (((333, 768), 1234, 0.05), ((64, 4096), 0x3FFFFFFFFFFFFFF1, 0.05), ((128, 256), 7, 0.5)):
+        got = F.dropout_mask(shape, seed, p, cuda_dev).cpu().numpy()
+        assert np.array_equal(got, dropout.keep_mask(shape, seed, p)), (shape, seed, p)

@@ -174,3 +174,26 @@ def test_golden_vectors():
         gold = torch.from_numpy(g[f"linear.{k}"]).view(torch.bfloat16).float()
         # fp32 BLAS summation order may differ between hosts: allow one bf16 ulp of the largest value
         assert rel_err(o[k], gold) <= 2.0 ** -7, k
+
+
+def test_dropout_mask_restatement_matches_the_product_source_and_is_well_behaved():
+    """oracle/dropout.py against the host compilation of csrc/b2q_internal.h's dropout_keep (the source the device
+    runs), plus the statistics a dropout mask needs (rate, no row / column / neighbour structure)."""
+    import subprocess
+
+    from oracle import build_c, dropout
+
+    exe = build_c.build_dropout_ref()
+    for seed, p, n in ((0, 0.05, 4096), (1234, 0.05, 5000), (0x3FFFFFFFFFFFFFFF, 0.5, 3000), (0x123456789ABCDEF, 0.01, 2048)):
+        out = subprocess.run([exe, str(seed), str(p), str(n)], capture_output=True, text=True, check=True).stdout.strip()
+        ref = np.frombuffer(out.encode(), dtype=np.uint8) - ord("0")
+        assert np.array_equal(ref, dropout.keep_mask((n,), seed, p)), (seed, p)
+    m = dropout.keep_mask((1024, 4096), 0x1234ABCD5678, 0.05).astype(np.float64)
+    d = 1.0 - m
+    assert abs(d.mean() - 0.05) < 5e-4
+    assert d.mean(1).std() < 1.5 * np.sqrt(0.05 * 0.95 / 4096) and d.mean(0).std() < 1.5 * np.sqrt(0.05 * 0.95 / 1024)
+    dc = d - d.mean()
+    for dr, dcol in ((0, 1), (0, 2), (0, 4), (0, 8), (1, 0)):
+        a = dc[: d.shape[0] - dr, : d.shape[1] - dcol]
+        b = dc[dr:, dcol:]
+        assert abs(float((a * b).mean() / dc.var())) < 5e-3, (dr, dcol)
