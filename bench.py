@@ -180,10 +180,24 @@ def main():
                          "for the CPU oracle)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+
+    def dump_state(why):
+        """Where is this rank?  Python stacks of every thread + the library's launch counter, on stderr (called from the
+        watchdog timers just before they give up, so a hung multi-GPU run leaves evidence behind)."""
+        import faulthandler
+        try:
+            n = sys.modules["b200qlora"].functional.launch_count() if "b200qlora" in sys.modules else -1
+        except Exception:  # noqa: BLE001 -- diagnostics must not raise
+            n = -1
+        print(f"[bench rank {rank}] state dump ({why}): b2q launches so far {n}", file=sys.stderr, flush=True)
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        sys.stderr.flush()
+
     if world > 1:
         # global safety net at N > 1: never hold a multi-GPU box for minutes if a rank gets stuck before `value` exists
         def global_timeout():
             print(f"[bench rank {rank}] no result after {args.global_timeout:.0f} s -- giving up", file=sys.stderr, flush=True)
+            dump_state("global timeout")
             os._exit(4)
         g = threading.Timer(args.global_timeout, global_timeout)
         g.daemon = True
@@ -307,6 +321,7 @@ def main():
     if world > 1 and not args.no_e2e:
         def e2e_timeout():
             mark("e2e phase timed out -- reporting `value` only")
+            dump_state("e2e timeout")
             if rank == 0:
                 print(result_line(None, None, None, note="e2e (module surface + host copies) did not finish within "
                                   f"{args.e2e_timeout:.0f} s at n_gpus={world}; value / roofline are device-timed and complete"),
@@ -316,8 +331,10 @@ def main():
         e2e_guard = threading.Timer(args.e2e_timeout, e2e_timeout)
         e2e_guard.daemon = True
         e2e_guard.start()
-        # hedge: run autograd on the calling thread at N > 1 (the hang appeared when backward first ran on engine threads)
-        torch.autograd.set_multithreading_enabled(False)
+        # hedge: run autograd on the calling thread at N > 1 (the hang appeared when backward first ran on engine threads);
+        # B2Q_E2E_AUTOGRAD_THREADS=1 keeps the engine threads (tools/gpu_multi_diag.sh)
+        if os.environ.get("B2Q_E2E_AUTOGRAD_THREADS") != "1":
+            torch.autograd.set_multithreading_enabled(False)
 
     # ---- e2e: module surface + host buffers ---------------------------------------------------
     e2e = None
@@ -335,6 +352,7 @@ def main():
             return t if width == t.shape[1] else torch.cat([t] * reps, dim=1)[:, :width].contiguous()
 
         trace = os.environ.get("B2Q_BENCH_TRACE") == "1"   # diagnostic: synchronise + mark after every phase
+        interleaved = world > 1 and os.environ.get("B2Q_E2E_ORDER") != "all_forward_then_backward"
 
         def tmark(what):
             if trace:
@@ -348,7 +366,7 @@ def main():
             ins = {k: widen(x, k) for k in widths_in}
             gos = {n: widen(dy, n) for n in widths_out}
             tmark("widen done")
-            g2 = stack.step_modules(ins, gos, tmark if trace else None, interleaved=(world > 1))
+            g2 = stack.step_modules(ins, gos, tmark if trace else None, interleaved=interleaved)
             tmark("step_modules done")
             host_out.copy_(g2.reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -373,7 +391,7 @@ def main():
             ems = float(t.item())
         e2e = {"value": M * world / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ems, "api": "LoraLinear4bit.forward + autograd (QLoRALinear) -> C ABI",
-               "order": "per-module forward+backward, single-threaded autograd (n_gpus > 1)" if world > 1
+               "order": "per-module forward+backward (n_gpus > 1)" if interleaved
                         else "forward of all modules, then backward of all"}
 
     # ---- the step either side of the path: fused clip + AdamW on the flat buckets (reported, not part of `value`) ---
