@@ -202,6 +202,10 @@ def main():
         g = threading.Timer(args.global_timeout, global_timeout)
         g.daemon = True
         g.start()
+        # last resort if the main thread is stuck while holding the GIL (the timers above then never run): faulthandler's
+        # watchdog is a C thread -- it dumps every Python stack and _exit(1)s without needing the interpreter
+        import faulthandler
+        faulthandler.dump_traceback_later(args.global_timeout + 30.0, exit=True, file=sys.stderr)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
@@ -429,6 +433,8 @@ def main():
                              "extrapolated linearly in FLOPs"}
         print(result_line(e2e, cpu, opt_info), flush=True)
     if world > 1:
+        import faulthandler
+        faulthandler.cancel_dump_traceback_later()
         dist.destroy_process_group()
 
 
