@@ -361,6 +361,26 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
         return 0;
     };
     auto slab = [&](int tile_m) { int g = static_cast<int>((32ll << 20) / (2ll * N * tile_m)); return g < 1 ? 1 : g; };
+    // Experiment hook (B2Q_DX_MASK_FIRST=1, variants 4/5 only, default off): write the masked LoRA term first with plain
+    // stores and let the decode GEMM's epilogue accumulate onto it with L2 reductions, instead of the other way round.
+    static const int mask_first_env = env_int("B2Q_DX_MASK_FIRST", 0);
+    const bool mask_first = masked && mask_first_env != 0 && variant >= 4;
+    auto masked_term = [&](int accumulate) -> int {
+        // LoRA dropout: dx (+)= keep * (du @ A) / (1 - p) -- masked epilogue; accumulate = reduce-add into dx at the L2
+        GemmParams q;
+        memset(&q, 0, sizeof(q));
+        q.D = dx; q.ldd = K; q.alpha = 1.0f / (1.0f - drop_p); q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
+        q.accum_d = accumulate;
+        q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.xf_ld = K;
+        int eq;
+        if ((eq = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return eq;
+        if ((eq = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return eq;
+        return launch<GemmKNMask>(q, stream);
+    };
+    if (mask_first) {
+        if ((e = masked_term(0))) return e;
+        p.accum_d = 1;
+    }
     switch (variant) {
         case 0: if ((e = setup(DxV0::BNC, slab(DxV0::TILE_M)))) return e; e = launch<DxV0>(p, stream); break;
         case 1: if ((e = setup(DxV1::BNC, slab(DxV1::TILE_M)))) return e; e = launch<DxV1>(p, stream); break;
@@ -373,16 +393,8 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
             break;
         default: if ((e = setup(DxV5::BNC, slab(DxV5::TILE_M)))) return e; e = launch<DxV5>(p, stream); break;
     }
-    if (e || !masked) return e;
-    // LoRA dropout: dx += keep * (du @ A) / (1 - p) -- masked epilogue, reduce-added into dx at the L2
-    GemmParams q;
-    memset(&q, 0, sizeof(q));
-    q.D = dx; q.ldd = K; q.alpha = 1.0f / (1.0f - drop_p); q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
-    q.accum_d = 1;
-    q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.xf_ld = K;
-    if ((e = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return e;
-    if ((e = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return e;
-    return launch<GemmKNMask>(q, stream);
+    if (e || !masked || mask_first) return e;
+    return masked_term(1);
 }
 
 template <int R>
