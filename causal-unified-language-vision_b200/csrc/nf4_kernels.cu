@@ -152,6 +152,111 @@ __global__ void __launch_bounds__(128, MINB) nf4_gemv_kernel(const __nv_bfloat16
         }
 }
 
+// Tensor-core formulation of the same GEMV (opt-in: B2Q_GEMV_CFG=3; not yet timed on hardware).  The SIMT kernel above
+// spends one FMA and one unpack per weight and token on top of the decode; here the decoded bf16x2 registers ARE the A
+// fragments of mma.sync.m16n8k16 (16 weight rows x 16 k), the tokens are the 8 columns of the B fragment, and the
+// accumulation costs no ALU work at any M <= 8.  A block owns 16 weight rows; its 8 warps take 128-weight k-steps in
+// turn (all of a warp's packed loads are in flight at once) and their fp32 partial sums are added in a fixed order
+// through shared memory (deterministic).  Lane (g = lane/4, t = lane%4) decodes the t-th 32-weight chunk of rows g and
+// g+8 in each k-step; MMA j of the step contracts weights 4j..4j+3 of every lane's chunk, i.e. the MMA's k index
+// {2t, 2t+1, 2t+8, 2t+9} stands for elements {4j, 4j+1, 4j+2, 4j+3} of chunk t -- the B fragment is loaded from x with
+// the same permutation, so the sum is over the true k.  Decoded weights are bit-identical to b2q_nf4_decode.
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int U>
+__global__ void __launch_bounds__(256, 2) nf4_gemv_mma_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const uint4* __restrict__ packed, AbsmaxSrc am,
+                                                              const float* __restrict__ code16_g,
+                                                              __nv_bfloat16* __restrict__ y, int M, int N, int K) {
+    __shared__ float red[8][128];
+    float code16[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) code16[i] = __ldg(code16_g + i);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int n0 = blockIdx.x * 16;
+    const int chunks = K / 32;              // 16-byte chunks (32 weights) per row
+    const int steps = (chunks + 3) / 4;     // k-steps of 4 chunks (one per t)
+    const int row_a = n0 + g, row_b = n0 + g + 8;
+    const bool ok_a = row_a < N, ok_b = row_b < N;
+    const bool tok = g < M;                 // column g of the B fragment is token g
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s0 = warp; s0 < steps; s0 += 8 * U) {
+        uint4 qa[U], qb[U];
+        float aa[U], ab[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = 4 * (s0 + 8 * u) + t;
+            const bool ok = c < chunks;     // also false for k-steps past the end
+            qa[u] = (ok && ok_a) ? __ldg(packed + static_cast<long long>(row_a) * chunks + c) : zero4;
+            qb[u] = (ok && ok_b) ? __ldg(packed + static_cast<long long>(row_b) * chunks + c) : zero4;
+            aa[u] = (ok && ok_a) ? load_absmax(am, static_cast<long long>(row_a) * (K / 64) + (c >> 1)) : 0.f;
+            ab[u] = (ok && ok_b) ? load_absmax(am, static_cast<long long>(row_b) * (K / 64) + (c >> 1)) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (s0 + 8 * u >= steps) break;             // warp-uniform
+            const int c = 4 * (s0 + 8 * u) + t;
+            uint32_t xr[16];                            // x[token g][c*32 .. c*32+31] as bf16x2 words
+            if (tok && c < chunks) {
+                const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<long long>(g) * K + c * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = __ldg(xp + i);
+                    xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) xr[i] = 0u;
+            }
+            uint32_t da[16], db[16];                    // 32 decoded weights of rows g and g+8, element order
+            {
+                Nf4Lut lut;
+                nf4_build_lut(code16, aa[u], lut);
+                const uint32_t w[4] = {qa[u].x, qa[u].y, qa[u].z, qa[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t o[4];
+                    nf4_decode_word(w[j], lut, o);
+                    da[4 * j] = o[0]; da[4 * j + 1] = o[1]; da[4 * j + 2] = o[2]; da[4 * j + 3] = o[3];
+                }
+            }
+            {
+                Nf4Lut lut;
+                nf4_build_lut(code16, ab[u], lut);
+                const uint32_t w[4] = {qb[u].x, qb[u].y, qb[u].z, qb[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t o[4];
+                    nf4_decode_word(w[j], lut, o);
+                    db[4 * j] = o[0]; db[4 * j + 1] = o[1]; db[4 * j + 2] = o[2]; db[4 * j + 3] = o[3];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                mma_bf16_m16n8k16(acc, da[2 * j], db[2 * j], da[2 * j + 1], db[2 * j + 1], xr[2 * j], xr[2 * j + 1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[warp][lane * 4 + i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        // accumulator element i of lane (gg, tt): row gg + 8 * (i >> 1), token 2 * tt + (i & 1)
+        const int ln = threadIdx.x >> 2, i = threadIdx.x & 3;
+        const int row = n0 + (ln >> 2) + 8 * (i >> 1), token = 2 * (ln & 3) + (i & 1);
+        if (token < M && row < N) y[static_cast<long long>(token) * N + row] = __float2bfloat16_rn(v);
+    }
+}
+
 // ---------------------------------------------------------------- quantise ----
 __device__ __forceinline__ uint32_t nf4_code_of(float x) {
     // number of thresholds strictly below x (== bitsandbytes' dQuantizeNF4 comparison tree); NaN -> 0
@@ -357,14 +462,16 @@ extern "C" int b2q_gemv_4bit(const void* x_bf16, const b2q_nf4_weight* w, void* 
     if (M < 0 || M > 8 || K % 64 != 0 || N <= 0) return B2Q_ERR_SHAPE;
     if (((reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(w->packed)) & 15) != 0) return B2Q_ERR_ARG;
     AbsmaxSrc am{w->absmax, w->absmax_q, w->absmax2, w->code256, w->offset};
-    static int cfg = -1;   // tuning hook: B2Q_GEMV_CFG = 0 (2 rows/warp, 2 in flight), 1 (1 row, 4 in flight, 8 blocks/SM), 2 (2 rows, 2, 6 blocks/SM)
+    static int cfg = -1;   // tuning hook: B2Q_GEMV_CFG = 0 (2 rows/warp, 2 in flight), 1 (1 row, 4 in flight, 8 blocks/SM), 2 (2 rows, 2, 6 blocks/SM), 3 (tensor-core formulation, opt-in)
     if (cfg < 0) { const char* e = getenv("B2Q_GEMV_CFG"); cfg = e ? atoi(e) : 1; }
     const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
     const uint4* pk = reinterpret_cast<const uint4*>(w->packed);
 #define B2Q_GEMV_LAUNCH(MR, RPW_, U_, MINB_) \
     nf4_gemv_kernel<MR, RPW_, U_, MINB_><<<(N + 4 * RPW_ - 1) / (4 * RPW_), 128, 0, stream>>>(x, pk, am, w->code16, y, M, N, K)
-    if (M == 1) {
+    if (cfg == 3) {
+        nf4_gemv_mma_kernel<4><<<(N + 15) / 16, 256, 0, stream>>>(x, pk, am, w->code16, y, M, N, K);
+    } else if (M == 1) {
         if (cfg == 0) B2Q_GEMV_LAUNCH(1, 2, 2, 1); else if (cfg == 2) B2Q_GEMV_LAUNCH(1, 2, 2, 6); else B2Q_GEMV_LAUNCH(1, 1, 4, 8);
     } else if (M <= 4) {
         if (cfg == 0) B2Q_GEMV_LAUNCH(4, 2, 2, 1); else B2Q_GEMV_LAUNCH(4, 2, 2, 4);
