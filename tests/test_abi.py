@@ -46,4 +46,12 @@ def test_sass_is_blackwell_native(lib_built):
     sass = subprocess.run(["cuobjdump", "-sass", lib_built], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "PRMT"):
         assert mnemonic in sass, mnemonic
-    assert "HMMA.16816" not in sass  # no legacy mma.sync path
+    # no legacy mma.sync path in any GEMM: the only kernel allowed to hold HMMA is the opt-in GEMV experiment, whose
+    # 8-token B fragment is the natural mma.sync shape and whose bound is HBM, not the tensor pipe
+    functions = sass.split("Function : ")[1:]
+    assert functions
+    import re
+
+    legacy = re.compile(r"(?<![A-Z])HMMA\.")   # mma.sync's HMMA.16816, not tcgen05's UTCHMMA
+    with_hmma = {f.split()[0] for f in functions if legacy.search(f)}
+    assert all("nf4_gemv_mma_kernel" in name for name in with_hmma), with_hmma
