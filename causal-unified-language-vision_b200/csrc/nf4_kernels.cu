@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(256) absmax_quantize_kernel(const float* __res
 }
 
 // ----------------------------------------------------------------- dropout ----
-// keep(m,k) = hash(seed, m*K + k) >= p * 2^32   (counter based, so forward, backward and the
-// oracle can all regenerate the same mask from (seed, p)).
+// keep(m,k) = 15-bit field of hash64(seed, (m*K + k) / 4) >= round(p * 2^15)   (b2q_internal.h dropout_keep; counter
+// based, so forward, backward and the oracle -- oracle/dropout.py -- all regenerate the same mask from (seed, p)).
 __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ mask, long long n,
                                                            unsigned long long seed, uint32_t thresh) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
