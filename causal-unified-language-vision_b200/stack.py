@@ -98,15 +98,26 @@ class QLoRALinearStack(nn.Module):
         return (base.weight.data, base.weight.quant_state, mod.lora_A[self.adapter].weight,
                 mod.lora_B[self.adapter].weight, mod.scaling[self.adapter])
 
-    def step_direct(self, recompute: bool = False) -> None:
+    def grad_sqnorm(self) -> torch.Tensor:
+        """Squared norm of all (reduced) LoRA gradients, a device scalar -- the step's read-back result in bench.py."""
+        total = None
+        for flat in self.sync.flat_grads():
+            v = flat.float().pow(2).sum()
+            total = v if total is None else total + v
+        return total
+
+    def step_direct(self, recompute: bool = False, inputs: Optional[dict] = None,
+                    grads_out: Optional[dict] = None) -> None:
         """Forward for all linears then backward for all, calling the C-ABI ops directly."""
         p = self.p
+        inputs = self.inputs if inputs is None else inputs
+        grads_out = self.grads_out if grads_out is None else grads_out
         self.sync.begin_step()
         saved = []
         base_seed = 7919 * self._step
         for i, mod in enumerate(self.mods):
             packed, qs, A, B, s = self._weights(mod)
-            x = self.inputs[A.shape[1]]
+            x = inputs[A.shape[1]]
             seed = base_seed + i
             u, us = F.lora_down(x, A, s, seed, p)
             y = F.qlora_fwd(x, packed, qs, us, B)
@@ -115,8 +126,8 @@ class QLoRALinearStack(nn.Module):
         for i in range(len(self.mods) - 1, -1, -1):
             mod = self.mods[i]
             packed, qs, A, B, s = self._weights(mod)
-            x = self.inputs[A.shape[1]]
-            dy = self.grads_out[B.shape[0]]
+            x = inputs[A.shape[1]]
+            dy = grads_out[B.shape[0]]
             u, seed = saved[i]
             if recompute:  # gradient checkpointing re-runs the forward inside backward (load_cullavo.py:91-93)
                 u, us = F.lora_down(x, A, s, seed, p)
@@ -150,11 +161,7 @@ class QLoRALinearStack(nn.Module):
                     trace(f"fwd+bwd down to module {i} done")
             self.sync.finish()
             self._step += 1
-            total = None
-            for flat in self.sync.flat_grads():
-                v = flat.float().pow(2).sum()
-                total = v if total is None else total + v
-            return total
+            return self.grad_sqnorm()
         outs = []
         for mod in self.mods:
             x = inputs[mod.in_features].detach().requires_grad_(True)
@@ -171,8 +178,4 @@ class QLoRALinearStack(nn.Module):
         if trace is not None:
             trace("grad sync done")
         self._step += 1
-        total = None
-        for flat in self.sync.flat_grads():
-            v = flat.float().pow(2).sum()
-            total = v if total is None else total + v
-        return total
+        return self.grad_sqnorm()
