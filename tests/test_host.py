@@ -166,3 +166,23 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.parametrize("extra", [[], ["--world", "2"], ["--world", "2", "--hang", "modules"]])
+def test_bench_control_flow_dry_run(extra):
+    """bench.py's phases, watchdog and JSON line with every device call stubbed (tests/dev_bench_dryrun.py): N = 1,
+    N > 1, and a module-surface step that never returns (the watchdog must print the line with the C-ABI e2e number)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "dev_bench_dryrun.py"), *extra], capture_output=True,
+                       text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if "--hang" in extra:
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+        d = json.loads(line)
+        assert d["e2e"]["api"].startswith("C-ABI") and "did not finish" in d["note"] and d["value"] > 0
+    else:
+        assert "dry run OK" in r.stdout
