@@ -11,11 +11,18 @@ seed (the mask is regenerated inside the kernels) -- never a decoded weight or a
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Optional
 
 import torch
 
 from . import functional as F
+
+
+def _device_guard(t: torch.Tensor):
+    """bitsandbytes' ``pre_call(A.device)``: the C ABI launches on the current device of the calling thread (backward runs
+    on an autograd engine thread).  Non-CUDA tensors pass through so that the functional layer raises its usual error."""
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
 def _flatten(x: torch.Tensor):
@@ -29,7 +36,7 @@ def _flatten(x: torch.Tensor):
 class MatMul4Bit(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, packed, qs):
-        with torch.cuda.device(x.device):   # bitsandbytes' pre_call(A.device): the C ABI launches on the current device
+        with _device_guard(x):
             x2, lead = _flatten(x)
             ctx.qs = qs
             ctx.lead = lead
@@ -43,7 +50,7 @@ class MatMul4Bit(torch.autograd.Function):
         (packed,) = ctx.saved_tensors
         dx = None
         if ctx.needs_input_grad[0]:
-            with torch.cuda.device(dy.device):   # backward may run on an autograd engine thread
+            with _device_guard(dy):
                 dy2, _ = _flatten(dy)
                 dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, None, None).reshape(*ctx.lead, -1).to(ctx.in_dtype)
         return dx, None, None
@@ -75,7 +82,7 @@ class QLoRALinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, packed, qs, A, B, scale, p, seed, grad_sink):
-        with torch.cuda.device(x.device):   # the C ABI launches on the current device of the calling thread
+        with _device_guard(x):
             return QLoRALinear._forward(ctx, x, packed, qs, A, B, scale, p, seed, grad_sink)
 
     @staticmethod
@@ -95,7 +102,7 @@ class QLoRALinear(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        with torch.cuda.device(dy.device):   # backward usually runs on an autograd engine thread
+        with _device_guard(dy):
             return QLoRALinear._backward(ctx, dy)
 
     @staticmethod
