@@ -66,6 +66,12 @@ SIGNATURES = {
     "b2q_sqnorm_partials": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
     "b2q_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_float, c_float, c_float, c_float,
                                c_float, c_i64, c_void_p, c_int, c_float, c_void_p]),
+    "b2q_comm_nccl_version": (c_int, []),
+    "b2q_comm_unique_id": (c_int, [c_void_p, c_size_t]),
+    "b2q_comm_init": (c_int, [ct.POINTER(c_void_p), c_void_p, c_size_t, c_int, c_int]),
+    "b2q_comm_allreduce_bucket": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
+    "b2q_comm_wait": (c_int, [c_void_p, c_void_p]),
+    "b2q_comm_destroy": (c_int, [c_void_p]),
     "b2q_set_variant": (c_int, [c_int, c_int]),
     "b2q_debug_set_trace": (c_int, [c_void_p, c_int]),
     "b2q_debug_set_prefetch": (c_int, [c_int]),

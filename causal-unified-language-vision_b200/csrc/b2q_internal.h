@@ -8,6 +8,9 @@
 
 namespace b2q {
 
+// Text behind b2q_last_error_detail() (defined in qlora_gemm.cu).
+void set_error_detail(const char* msg);
+
 // Counter-based keep/drop decision shared by every kernel that needs the LoRA-dropout mask, by the stand-alone
 // mask kernel and (through it) by the CPU oracle.  One call of a 4-round Philox-2x32 style mixer on
 // (counter = i >> 2, key = seed) yields 64 bits = four 15-bit fields (the low 15 bits of each 16-bit quarter) for four

@@ -10,6 +10,7 @@ namespace b2q {
 
 std::atomic<uint64_t> g_launch_count{0};
 static char g_last_error[512] = "";
+void set_error_detail(const char* msg) { snprintf(g_last_error, sizeof(g_last_error), "%s", msg); }
 
 // ---------------------------------------------------------------- tensor maps ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -268,6 +269,7 @@ extern "C" const char* b2q_error_string(int code) {
         case B2Q_ERR_ARG: return "b2q: invalid pointer arguments";
         case B2Q_ERR_DRIVER: return "b2q: CUDA driver tensor-map encode unavailable or failed";
         case B2Q_ERR_WORKSPACE: return "b2q: workspace too small";
+        case B2Q_ERR_COMM: return "b2q: NCCL unavailable or an NCCL call failed";
         default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "b2q: unknown error";
     }
 }

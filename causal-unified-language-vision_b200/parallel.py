@@ -20,6 +20,11 @@ Design (one process per GPU, weights replicated, batch sharded):
   * ``overlap=False`` (default since the end of round 1, see DESIGN.md "open issue"): ``finish()`` issues
     the all-reduces of all buckets on the compute stream -- 360 MB per step, < 1 ms on NVLink.
 The same class runs on CPU tensors with the ``gloo`` backend (SUM then divide) for tests.
+
+``backend="b2q"`` (or ``B2Q_COMM_BACKEND=b2q``) issues the bucket all-reduces through the library's own C-ABI
+communicator (``b2q_comm_*`` in include/b2q.h: NCCL resolved with dlopen, the same entry points a host without a torch
+process group would bind) instead of ``torch.distributed``; the unique id travels over the existing process group.
+Compiled and exported, default off: it has not been exercised on hardware yet.
 """
 from __future__ import annotations
 
@@ -56,7 +61,8 @@ class _Bucket:
 
 class GradSync:
     def __init__(self, modules: Sequence, adapter_name: str, process_group=None, bucket_bytes: int = 64 << 20,
-                 grad_dtype: torch.dtype = torch.bfloat16, install: bool = True, overlap: Optional[bool] = None):
+                 grad_dtype: torch.dtype = torch.bfloat16, install: bool = True, overlap: Optional[bool] = None,
+                 backend: Optional[str] = None):
         """``modules``: the LoRA-wrapped linears in FORWARD order (``LoraLinear4bit`` or anything with
         ``lora_A[adapter].weight`` / ``lora_B[adapter].weight``)."""
         # overlap=True: a bucket's all-reduce is issued on a side stream as soon as its last gradient kernel is enqueued
@@ -118,10 +124,46 @@ class GradSync:
         self._use_cuda = device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=device) if self._use_cuda else None
         self._done_events = []
+        if backend is None:
+            import os
+            backend = os.environ.get("B2Q_COMM_BACKEND", "torch")
+        if backend not in ("torch", "b2q"):
+            raise ValueError(f"unknown gradient-sync backend {backend!r}")
+        self.backend = backend
+        self._comm = None
+        if backend == "b2q" and self.world > 1:
+            if not self._use_cuda:
+                raise ValueError("backend='b2q' is the NCCL communicator of libb2q.so: CUDA buckets only")
+            self._init_b2q_comm()
         if install:
             for m in self.modules:
                 m._grad_sinks[adapter_name] = self
         self.begin_step()
+
+    def _init_b2q_comm(self) -> None:
+        import ctypes as ct
+
+        from . import _lib
+        lib = _lib.load()
+        rank = dist.get_rank(self.group)
+        ids = [None]
+        if rank == 0:
+            buf = ct.create_string_buffer(128)
+            _lib.check(lib.b2q_comm_unique_id(buf, 128), "b2q_comm_unique_id")
+            ids[0] = buf.raw
+        dist.broadcast_object_list(ids, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                   group=self.group)
+        comm = ct.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.b2q_comm_init(ct.byref(comm), ids[0], 128, self.world, rank), "b2q_comm_init")
+        self._comm = comm
+
+    def close(self) -> None:
+        """Destroy the library communicator (backend='b2q'); the torch backend owns nothing."""
+        if self._comm is not None:
+            from . import _lib
+            _lib.check(_lib.load().b2q_comm_destroy(self._comm), "b2q_comm_destroy")
+            self._comm = None
 
     # ---- per step -----------------------------------------------------------------------
     def begin_step(self) -> None:
@@ -155,7 +197,15 @@ class GradSync:
     defer = False  # True while accumulating micro-batches: reduce only on the last one
 
     def _launch(self, b: _Bucket) -> None:
-        if self._use_cuda and not self.overlap:
+        if self._comm is not None:
+            from . import _lib
+            dtype = {torch.bfloat16: 0, torch.float32: 1}[b.flat.dtype]
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.load().b2q_comm_allreduce_bucket(self._comm, b.flat.data_ptr(), b.flat.numel(), dtype,
+                                                                 1 if self.overlap else 0, stream),
+                           "b2q_comm_allreduce_bucket")
+        elif self._use_cuda and not self.overlap:
             dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.group)   # on the compute stream, in order
         elif self._use_cuda:
             ev = torch.cuda.Event()
@@ -187,6 +237,9 @@ class GradSync:
             cur = torch.cuda.current_stream(self.device)
             for ev in self._done_events:
                 cur.wait_event(ev)
+            if self._comm is not None:
+                from . import _lib
+                _lib.check(_lib.load().b2q_comm_wait(self._comm, cur.cuda_stream), "b2q_comm_wait")
         self._done_events = []
 
     # ---- helpers ------------------------------------------------------------------------

@@ -41,6 +41,7 @@ typedef struct CUstream_st* cudaStream_t;
 #define B2Q_ERR_ARG (-2)     /* null / inconsistent pointer arguments             */
 #define B2Q_ERR_DRIVER (-3)  /* CUDA driver entry point (tensor-map encode) failed */
 #define B2Q_ERR_WORKSPACE (-4) /* workspace too small                             */
+#define B2Q_ERR_COMM (-5)    /* NCCL not loadable, or an NCCL call failed (see b2q_last_error_detail) */
 
 /* One NF4-quantised weight W[N,K] (blocksize 64).  Exactly one of absmax / absmax_q is set. */
 typedef struct b2q_nf4_weight {
@@ -175,6 +176,33 @@ int b2q_sqnorm_partials(const void* g_bf16, int64_t n, float* partials, cudaStre
 int b2q_adamw_step(void* p_bf16, const void* g_bf16, void* m, void* v, int state_is_f32, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int64_t step, const float* sq_partials,
                    int n_partials, float max_norm, cudaStream_t stream);
+
+/* ---- data-parallel exchange of the LoRA-gradient buckets (NCCL over NVLink 5 / NVSwitch) --- *
+ * Replaces the DDP reducer that `accel.prepare` installs and `accel.backward` is meant to drive
+ * (trainer/utils_trainer.py:32-37, trainer/default_trainer.py:83-84): one all-reduce(mean) per flat bucket that
+ * b2q_lora_grads wrote, issued as soon as the bucket is complete.  The Python host layer uses torch.distributed for the
+ * same exchange by default (parallel.GradSync); these entry points are the same step for a host that has no torch
+ * process group (GradSync(backend="b2q") drives them too).  NCCL is dlopen()ed on first use (libnccl.so.2; inside a
+ * torch process that is the copy torch already loaded).  One communicator per process and GPU; calls on one
+ * communicator must come from one thread at a time. */
+#define B2Q_COMM_ID_BYTES 128
+#define B2Q_DTYPE_BF16 0
+#define B2Q_DTYPE_F32 1
+typedef struct b2q_comm b2q_comm;
+/* NCCL's version code (e.g. 22809), or B2Q_ERR_COMM when the library cannot be loaded. */
+int b2q_comm_nccl_version(void);
+/* Rank 0: fill id_out (B2Q_COMM_ID_BYTES bytes), then hand the bytes to every rank by any means. */
+int b2q_comm_unique_id(void* id_out, size_t id_bytes);
+/* Collective over all ranks: communicator bound to the calling thread's current device. */
+int b2q_comm_init(b2q_comm** comm_out, const void* id, size_t id_bytes, int nranks, int rank);
+/* bucket[i] = mean over ranks of bucket[i], in place (count elements of dtype B2Q_DTYPE_*).
+ * overlap = 0: enqueued on `stream`, in order.  overlap = 1: enqueued on the communicator's own stream after everything
+ * enqueued on `stream` so far, so it runs concurrently with the kernels that follow on `stream`; call b2q_comm_wait
+ * before anything reads the bucket. */
+int b2q_comm_allreduce_bucket(b2q_comm* comm, void* bucket, int64_t count, int dtype, int overlap, cudaStream_t stream);
+/* `stream` waits (on the device, no host block) for every overlapped all-reduce issued so far. */
+int b2q_comm_wait(b2q_comm* comm, cudaStream_t stream);
+int b2q_comm_destroy(b2q_comm* comm);
 
 /* Debug / profiling: when buf != NULL every following tcgen05 GEMM launch records clock64 stamps of its
  * pipeline phases for the first `tiles_per_cta` tiles of every CTA into buf[cta][tile][8] (int64):

@@ -55,3 +55,24 @@ def test_sass_is_blackwell_native(lib_built):
     legacy = re.compile(r"(?<![A-Z])HMMA\.")   # mma.sync's HMMA.16816, not tcgen05's UTCHMMA
     with_hmma = {f.split()[0] for f in functions if legacy.search(f)}
     assert all("nf4_gemv_mma_kernel" in name for name in with_hmma), with_hmma
+
+
+def test_comm_entry_points_without_a_gpu(lib_built):
+    """b2q_comm_*: argument checking and NCCL resolution (dlopen) work on a machine without a GPU; no collective is run."""
+    import ctypes as ct
+
+    import b200qlora as q
+
+    lib = q._lib.load()
+    assert lib.b2q_comm_unique_id(None, 0) == -2 and lib.b2q_comm_wait(None, None) == -2
+    assert lib.b2q_comm_allreduce_bucket(None, None, 0, 0, 0, None) == -2
+    assert lib.b2q_comm_destroy(None) == 0
+    comm = ct.c_void_p()
+    assert lib.b2q_comm_init(ct.byref(comm), None, 0, 2, 0) == -2
+    v = lib.b2q_comm_nccl_version()
+    assert v == -5 or v >= 21800, v          # B2Q_ERR_COMM if no libnccl.so.2 can be found, else NCCL's version code
+    if v > 0:
+        import torch  # noqa: F401 -- torch is loaded, so dlopen must have returned torch's own NCCL
+
+        assert v == torch.cuda.nccl.version()[0] * 10000 + torch.cuda.nccl.version()[1] * 100 + torch.cuda.nccl.version()[2]
+        assert b"NCCL" in lib.b2q_error_string(-5)
