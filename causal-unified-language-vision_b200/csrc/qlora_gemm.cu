@@ -111,15 +111,23 @@ static int map_bf16_out(CUtensorMap* m, const void* base, int rows, int cols, lo
     return 0;
 }
 
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
+// SM count of the calling thread's current device (cached per device: one process may drive several GPUs)
 static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    static int cache[64] = {0};
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+        cache[dev] = n > 0 ? n : 148;
     }
-    return n;
+    return cache[dev];
 }
 
 // Row stride of the 128-row tiles of a skinny kernel such that one wave covers the SMs as evenly as possible
@@ -162,12 +170,14 @@ static int g_pdl = -1;   // -1: read B2Q_PDL (default off)
 
 template <class Cfg>
 static int launch(GemmParams& p, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};   // per device: the opt-in to > 48 KB of dynamic shared memory is per context
+    const int dev = current_device();
+    const uint64_t bit = 1ull << (dev & 63);
+    if ((attr_set.load(std::memory_order_relaxed) & bit) == 0) {
         cudaError_t e = cudaFuncSetAttribute(qlora_gemm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return static_cast<int>(e);
-        attr_set = true;
+        attr_set.fetch_or(bit, std::memory_order_relaxed);
     }
     if (g_pdl < 0) { const char* v = getenv("B2Q_PDL"); g_pdl = v ? atoi(v) : 0; }   // opt-in: no measurable gain
     p.trace = g_trace;
