@@ -59,9 +59,20 @@ def _stream():
 
 
 def _need_cuda(*tensors):
+    """Every tensor on the GPU, and on the calling thread's CURRENT device: the C ABI launches on the current device's
+    stream (bitsandbytes asserts the same with ``is_on_gpu`` and switches with ``pre_call``; the autograd Functions in
+    autograd.py do the switch, direct callers must)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("b2q ops run on the GPU only (sm_100a); got a CPU tensor and there is no CPU fallback")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"tensor on {t.device} but the current CUDA device is cuda:{cur}: wrap the call in "
+                               "`with torch.cuda.device(tensor.device):`")
 
 
 def _need(t: torch.Tensor, dtype, name: str):
