@@ -434,3 +434,15 @@ def test_dropout_mask_matches_cpu_restatement(F, cuda_dev):
     for shape, seed, p in (((333, 768), 1234, 0.05), ((64, 4096), 0x3FFFFFFFFFFFFFF1, 0.05), ((128, 256), 7, 0.5)):
         got = F.dropout_mask(shape, seed, p, cuda_dev).cpu().numpy()
         assert np.array_equal(got, dropout.keep_mask(shape, seed, p)), (shape, seed, p)
+
+
+def test_dropout_mask_golden_fixture_on_gpu(F, cuda_dev):
+    """The exported GPU mask reproduces the committed fixture (tests/golden/dropout_mask_golden.json) bit for bit."""
+    import hashlib
+    import json
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dropout_mask_golden.json")
+    for c in json.load(open(path))["cases"]:
+        m = F.dropout_mask(tuple(c["shape"]), c["seed"], c["p"], cuda_dev).cpu().numpy()
+        assert int(m.sum()) == c["kept"]
+        assert hashlib.sha256(np.packbits(m).tobytes()).hexdigest() == c["sha256"], c

@@ -197,3 +197,17 @@ def test_dropout_mask_restatement_matches_the_product_source_and_is_well_behaved
         a = dc[: d.shape[0] - dr, : d.shape[1] - dcol]
         b = dc[dr:, dcol:]
         assert abs(float((a * b).mean() / dc.var())) < 5e-3, (dr, dcol)
+
+
+def test_dropout_mask_golden_fixture():
+    """tests/golden/dropout_mask_golden.json (oracle/make_dropout_golden.py) pins the mask definition against drift."""
+    import hashlib
+
+    from oracle import dropout
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dropout_mask_golden.json")
+    for c in json.load(open(path))["cases"]:
+        m = dropout.keep_mask(tuple(c["shape"]), c["seed"], c["p"])
+        assert int(m.sum()) == c["kept"]
+        assert np.packbits(m.reshape(c["shape"])[0][:64]).tobytes().hex() == c["first_row_hex"]
+        assert hashlib.sha256(np.packbits(m).tobytes()).hexdigest() == c["sha256"]
