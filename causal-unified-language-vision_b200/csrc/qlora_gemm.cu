@@ -249,6 +249,9 @@ using FwdV4 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, 1
 using DxV4 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, 1>;
 using FwdV5 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, -1>;
 using DxV5 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, -1>;
+// experiment (variant 6, opt-in): V5 with the UMMA issuer running sub-tile 0 three k-blocks ahead at the start of a tile
+using FwdV6 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, -1, 1, 3>;
+using DxV6 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, -1, 1, 3>;
 
 template <int R> constexpr int skinny_stages() { return 6; }
 template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>()>;   // u = x A^T
@@ -339,6 +342,10 @@ extern "C" int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void*
         if ((e = setup(FwdV4::BNC, slab(FwdV4::TILE_M)))) return e;
         return launch<FwdV4>(p, stream);
     }
+    if (variant == 6) {
+        if ((e = setup(FwdV6::BNC, slab(FwdV6::TILE_M)))) return e;
+        return launch<FwdV6>(p, stream);
+    }
     if ((e = setup(FwdV5::BNC, slab(FwdV5::TILE_M)))) return e;
     return launch<FwdV5>(p, stream);
 }
@@ -403,6 +410,7 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
             if ((e = setup(DxV4::BNC, slab(DxV4::TILE_M)))) return e;
             e = launch<DxV4>(p, stream);
             break;
+        case 6: if ((e = setup(DxV6::BNC, slab(DxV6::TILE_M)))) return e; e = launch<DxV6>(p, stream); break;
         default: if ((e = setup(DxV5::BNC, slab(DxV5::TILE_M)))) return e; e = launch<DxV5>(p, stream); break;
     }
     if (e || !masked || mask_first) return e;

@@ -113,8 +113,12 @@ CASES = [  # M, N, K, r, double_quant
 ]
 
 
+# variant 6 (run-ahead issue order) is an experiment that has not run on hardware yet: B2Q_EXPERIMENTAL=1 adds it
+VARIANTS = [0, 1, 2, 3, 4, 5] + ([6] if os.environ.get("B2Q_EXPERIMENTAL") == "1" else [])
+
+
 @pytest.mark.parametrize("M,N,K,r,dq", CASES)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_linear_fwd_bwd_against_oracle(F, cuda_dev, M, N, K, r, dq, variant):
     from oracle.qlora import make_case, qlora_linear_fwd_bwd, rel_err
 
@@ -446,3 +450,23 @@ def test_dropout_mask_golden_fixture_on_gpu(F, cuda_dev):
         m = F.dropout_mask(tuple(c["shape"]), c["seed"], c["p"], cuda_dev).cpu().numpy()
         assert int(m.sum()) == c["kept"]
         assert hashlib.sha256(np.packbits(m).tobytes()).hexdigest() == c["sha256"], c
+
+
+@pytest.mark.skipif(os.environ.get("B2Q_EXPERIMENTAL") != "1", reason="experiments not yet run on hardware (B2Q_EXPERIMENTAL=1)")
+def test_experimental_variant6_bit_identical_to_default(F, cuda_dev):
+    """Variant 6 issues the same MMAs in the same order per accumulator element: outputs must equal variant 5 bit for bit."""
+    stackmod = importlib.import_module("causal-unified-language-vision_b200.stack")
+    gen = torch.Generator(device=cuda_dev).manual_seed(3)
+    lin = stackmod.make_quantized_linear(1024, 2048, cuda_dev, gen)
+    packed, qs = lin.weight.data, lin.weight.quant_state
+    x = torch.randn(1536, 2048, device=cuda_dev, dtype=torch.bfloat16)
+    dy = torch.randn(1536, 1024, device=cuda_dev, dtype=torch.bfloat16)
+    outs = {}
+    for v in (5, 6):
+        F.set_variant(v, v)
+        try:
+            outs[v] = (F.qlora_fwd(x, packed, qs, None, None), F.qlora_bwd_dx(dy, packed, qs, None, None))
+            torch.cuda.synchronize()
+        finally:
+            F.set_variant(-1, -1)
+    assert torch.equal(outs[5][0], outs[6][0]) and torch.equal(outs[5][1], outs[6][1])
