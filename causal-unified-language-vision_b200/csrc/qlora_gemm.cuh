@@ -77,13 +77,15 @@ struct GemmParams {
 template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_, int NG_ = 2,
           int PST_ = 6, bool A_XF_ = false, int STG_ = 0, int ESETS_ = 1, int RA_ = 0>
 struct GemmCfg {
-    // RA > 0 (experiment, MT == 2 with a single accumulator stage): at the start of a tile the UMMA issuer runs the first
-    // RA k-blocks of sub-tile 0 ahead -- as soon as the epilogue has drained sub-tile 0 of the previous tile -- and
-    // issues the same k-blocks of sub-tile 1 (and releases their operand stages) once sub-tile 1 is drained too, so the
-    // tensor pipe works through most of sub-tile 1's drain instead of one k-block of it.  Same MMAs, same order per
-    // accumulator element: results are bit-identical to RA == 0.
+    // RA > 0 (experiment, MT == 2 with a single accumulator stage): the UMMA issuer reorders the first and the last RA
+    // k-blocks of a tile.  Head: sub-tile 0 of the first RA k-blocks as soon as the epilogue has drained sub-tile 0 of the
+    // previous tile, then sub-tile 1 of the same k-blocks (releasing their operand stages) once sub-tile 1 is drained
+    // too.  Tail: sub-tile 0 of the last RA k-blocks first and a separate "sub-tile 0 complete" commit, so the epilogue
+    // drains sub-tile 0 while the tensor pipe finishes sub-tile 1.  The pipe then idles ~2.9 k instead of ~5.5 k cycles
+    // per 84 k-cycle tile.  Same MMAs, same order per accumulator element: results are bit-identical to RA == 0.
     static constexpr int RA = RA_;
-    static_assert(RA_ == 0 || (MT_ == 2 && 2 * MT_ * BN_ > 512 && RA_ < STAGES_ && !A_XF_), "run-ahead: two sub-tiles, one accumulator stage");
+    static_assert(RA_ == 0 || (MT_ == 2 && 2 * MT_ * BN_ > 512 && RA_ < STAGES_ && !A_XF_ && STG_ != 0),
+                  "run-ahead: two sub-tiles, one accumulator stage, staged epilogue");
     // ESETS = 2: two sets of four epilogue warps (4-7 and 8-11), one per accumulator stage, for kernels that are all
     // epilogue (one k-block per tile): set e drains the tiles whose sequence number is e (mod 2).
     static constexpr int ESETS = ESETS_;
@@ -187,7 +189,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     auto pk_bar = [&](int s) { return bar_base + 8u * (NB0 + s); };
     auto pk_empty_bar = [&](int s) { return bar_base + 8u * (NB0 + PST + s); };
     auto xf_bar = [&](int s) { return bar_base + 8u * (NB0 + 2 * PST + s); };
-    constexpr int NBARS = NB0 + 2 * PST + (Cfg::A_XF ? STAGES : 0);
+    // RA configs: tfull_bar(a) = "sub-tile 0 complete", tfull1_bar(a) = "sub-tile 1 complete" (see the UMMA issuer)
+    constexpr int NB1 = NB0 + 2 * PST + (Cfg::A_XF ? STAGES : 0);
+    [[maybe_unused]] auto tfull1_bar = [&](int a) { return bar_base + 8u * (NB1 + a); };
+    constexpr int NBARS = NB1 + (Cfg::RA > 0 ? ACC_STAGES : 0);
     static_assert(8 * NBARS + 8 <= Cfg::BAR_BYTES, "barrier area");
     const uint32_t tmem_slot = bar_base + 8u * NBARS;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + 8 * NBARS);
@@ -227,6 +232,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             mbar_init(pk_empty_bar(s), Cfg::NDW);         // decode warps, once the bytes are in registers
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
+            if constexpr (Cfg::RA > 0) mbar_init(tfull1_bar(a), 1);
             mbar_init(tfull_bar(a), 1);                   // tcgen05.commit
             for (int mt = 0; mt < MT; ++mt) mbar_init(tempty_bar(a, mt), CG * 4);  // one arrive per epilogue warp, both CTAs
         }
@@ -329,40 +335,36 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 long long* tr = (p.trace != nullptr && tseq < p.trace_tiles)
                                     ? p.trace + (static_cast<long long>(blockIdx.x) * p.trace_tiles + tseq) * 8 : nullptr;
                 long long full_wait = 0;
-                auto issue_mt = [&](int s_, int mt, int kb) {   // the four k=16 MMAs of (stage s_, sub-tile mt)
-                    const uint64_t a_base = Cfg::A_MN ? umma_desc_sw128(a_stage(s_), 8192, 1024) : umma_desc_sw128(a_stage(s_), 16, 1024);
-                    const uint64_t b_base = Cfg::B_MN ? umma_desc_sw128(b_stage(s_), 8192, 1024) : umma_desc_sw128(b_stage(s_), 16, 1024);
-                    const uint32_t d_tmem = tmem_base + as * ACC_COLS + mt * BN;
-                    // descriptors of (stage, mt, k) = descriptor of the stage base + a constant in the address field
-                    // (the stage bases are 1024-byte aligned and the offsets stay far below the 14-bit field)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t adesc = a_base + static_cast<uint64_t>((mt * 16384 + k * (Cfg::A_MN ? 2048 : 32)) >> 4);
-                        const uint64_t bdesc = b_base + static_cast<uint64_t>((k * (Cfg::B_MN ? 2048 : 32)) >> 4);
-                        umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    }
-                };
-                int kb_begin = 0;
-                if constexpr (Cfg::RA > 0) {
-                    // run-ahead: sub-tile 0 of k-blocks [0, ra) first, then sub-tile 1 of the same k-blocks
-                    const int ra = kb_total < Cfg::RA ? kb_total : Cfg::RA;
-                    if (tr != nullptr) tr[0] = tr[1] = clock64();
-                    mbar_wait(tempty_bar(as, 0), aph ^ 1u);
-                    tc_fence_after();
-                    if (tr != nullptr) tr[2] = clock64();
-                    int s2 = s;
-                    for (int kb = 0; kb < ra; ++kb) {
-                        // (ra < STAGES: the ring does not wrap inside the window more than once, the phase flips with s2)
-                        mbar_wait(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph);
+                if constexpr (Cfg::RA == 0) {
+                    for (int kb = 0; kb < kb_total; ++kb) {
+                        long long w0 = 0;
+                        if (tr != nullptr) {
+                            w0 = clock64();
+                            if (kb == 0) tr[0] = w0;
+                        }
+                        mbar_wait(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph);
                         tc_fence_after();
-                        issue_mt(s2, 0, kb);
-                        if (++s2 == STAGES) s2 = 0;
-                    }
-                    mbar_wait(tempty_bar(as, 1), aph ^ 1u);
-                    tc_fence_after();
-                    if (tr != nullptr) tr[3] = clock64();
-                    for (int kb = 0; kb < ra; ++kb) {
-                        issue_mt(s, 1, kb);
+                        if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
+                        const uint64_t a_base = Cfg::A_MN ? umma_desc_sw128(a_stage(s), 8192, 1024) : umma_desc_sw128(a_stage(s), 16, 1024);
+                        const uint64_t b_base = Cfg::B_MN ? umma_desc_sw128(b_stage(s), 8192, 1024) : umma_desc_sw128(b_stage(s), 16, 1024);
+    #pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
+                                if (tr != nullptr && mt == 0) tr[1] = clock64();
+                                mbar_wait(tempty_bar(as, mt), aph ^ 1u);
+                                tc_fence_after();
+                                if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
+                            }
+                            const uint32_t d_tmem = tmem_base + as * ACC_COLS + mt * BN;
+                            // descriptors of (stage, mt, k) = descriptor of the stage base + a constant in the address field
+                            // (the stage bases are 1024-byte aligned and the offsets stay far below the 14-bit field)
+    #pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t adesc = a_base + static_cast<uint64_t>((mt * 16384 + k * (Cfg::A_MN ? 2048 : 32)) >> 4);
+                                const uint64_t bdesc = b_base + static_cast<uint64_t>((k * (Cfg::B_MN ? 2048 : 32)) >> 4);
+                                umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
                         umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
                         if (kb == kb_total - 1) {
                             umma_commit<CG>(tfull_bar(as));
@@ -370,33 +372,105 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         }
                         if (++s == STAGES) { s = 0; ph ^= 1u; }
                     }
-                    kb_begin = ra;
-                }
-                for (int kb = kb_begin; kb < kb_total; ++kb) {
-                    long long w0 = 0;
-                    if (tr != nullptr) {
-                        w0 = clock64();
-                        if (kb == 0) tr[0] = w0;
-                    }
-                    mbar_wait(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph);
-                    tc_fence_after();
-                    if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
-                            if (tr != nullptr && mt == 0) tr[1] = clock64();
-                            mbar_wait(tempty_bar(as, mt), aph ^ 1u);
-                            tc_fence_after();
-                            if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
+                } else {
+                    auto issue_mt = [&](int s_, int mt, int kb) {   // the four k=16 MMAs of (stage s_, sub-tile mt)
+                        const uint64_t a_base = Cfg::A_MN ? umma_desc_sw128(a_stage(s_), 8192, 1024) : umma_desc_sw128(a_stage(s_), 16, 1024);
+                        const uint64_t b_base = Cfg::B_MN ? umma_desc_sw128(b_stage(s_), 8192, 1024) : umma_desc_sw128(b_stage(s_), 16, 1024);
+                        const uint32_t d_tmem = tmem_base + as * ACC_COLS + mt * BN;
+                        // descriptors of (stage, mt, k) = descriptor of the stage base + a constant in the address field
+                        // (the stage bases are 1024-byte aligned and the offsets stay far below the 14-bit field)
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adesc = a_base + static_cast<uint64_t>((mt * 16384 + k * (Cfg::A_MN ? 2048 : 32)) >> 4);
+                            const uint64_t bdesc = b_base + static_cast<uint64_t>((k * (Cfg::B_MN ? 2048 : 32)) >> 4);
+                            umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         }
-                        issue_mt(s, mt, kb);
+                    };
+                    int kb_begin = 0, kb_end = kb_total;
+                    if constexpr (Cfg::RA > 0) {
+                        // Head: sub-tile 0 of k-blocks [0, ra) as soon as ITS accumulator is drained, then sub-tile 1 of the
+                        // same k-blocks once sub-tile 1 is drained too (the operand stages are released in the second pass).
+                        const int ra = kb_total < Cfg::RA ? kb_total : Cfg::RA;
+                        const int rt = (kb_total - ra) < Cfg::RA ? (kb_total - ra) : Cfg::RA;   // tail window, see below
+                        if (tr != nullptr) tr[0] = tr[1] = clock64();
+                        mbar_wait(tempty_bar(as, 0), aph ^ 1u);
+                        tc_fence_after();
+                        if (tr != nullptr) tr[2] = clock64();
+                        int s2 = s;
+                        for (int kb = 0; kb < ra; ++kb) {
+                            // (ra < STAGES: the window wraps the ring at most once; a wrapped stage is one phase further)
+                            mbar_wait(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph);
+                            tc_fence_after();
+                            issue_mt(s2, 0, kb);
+                            if (kb == kb_total - 1) umma_commit<CG>(tfull_bar(as));
+                            if (++s2 == STAGES) s2 = 0;
+                        }
+                        mbar_wait(tempty_bar(as, 1), aph ^ 1u);
+                        tc_fence_after();
+                        if (tr != nullptr) tr[3] = clock64();
+                        for (int kb = 0; kb < ra; ++kb) {
+                            issue_mt(s, 1, kb);
+                            umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
+                            if (kb == kb_total - 1) {
+                                umma_commit<CG>(tfull1_bar(as));
+                                if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
+                            }
+                            if (++s == STAGES) { s = 0; ph ^= 1u; }
+                        }
+                        kb_begin = ra;
+                        kb_end = kb_total - rt;
                     }
-                    umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
-                    if (kb == kb_total - 1) {
-                        umma_commit<CG>(tfull_bar(as));
-                        if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
+                    for (int kb = kb_begin; kb < kb_end; ++kb) {
+                        long long w0 = 0;
+                        if (tr != nullptr) {
+                            w0 = clock64();
+                            if (kb == 0) tr[0] = w0;
+                        }
+                        mbar_wait(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph);
+                        tc_fence_after();
+                        if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
+    #pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
+                                if (tr != nullptr && mt == 0) tr[1] = clock64();
+                                mbar_wait(tempty_bar(as, mt), aph ^ 1u);
+                                tc_fence_after();
+                                if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
+                            }
+                            issue_mt(s, mt, kb);
+                            if constexpr (Cfg::RA > 0) {
+                                if (mt == 0 && kb == kb_total - 1) umma_commit<CG>(tfull_bar(as));
+                            }
+                        }
+                        umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
+                        if (kb == kb_total - 1) {
+                            if constexpr (Cfg::RA > 0) umma_commit<CG>(tfull1_bar(as)); else umma_commit<CG>(tfull_bar(as));
+                            if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
+                        }
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
                     }
-                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    if constexpr (Cfg::RA > 0) {
+                        // Tail: the last rt k-blocks of sub-tile 0 first, so that the epilogue drains sub-tile 0 while the
+                        // tensor pipe still works on sub-tile 1 of the same k-blocks.
+                        const int rt = kb_total - kb_end;
+                        if (rt > 0) {
+                            int s2 = s;
+                            for (int kb = kb_end; kb < kb_total; ++kb) {
+                                mbar_wait(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph);
+                                tc_fence_after();
+                                issue_mt(s2, 0, kb);
+                                if (++s2 == STAGES) s2 = 0;
+                            }
+                            umma_commit<CG>(tfull_bar(as));
+                            for (int kb = kb_end; kb < kb_total; ++kb) {
+                                issue_mt(s, 1, kb);
+                                umma_commit<CG>(empty_bar(s));
+                                if (++s == STAGES) { s = 0; ph ^= 1u; }
+                            }
+                            umma_commit<CG>(tfull1_bar(as));
+                            if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
+                        }
+                    }
                 }
                 if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
             }
@@ -457,6 +531,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
 #pragma unroll 1
                 for (int q = 0; q < NG64; ++q) {
                     const int mt = q / GPM, c = q % GPM;
+                    if constexpr (Cfg::RA > 0) {
+                        if (q == GPM) {   // first group of sub-tile 1: its MMAs are committed separately
+                            mbar_wait(tfull1_bar(as), aph);
+                            tc_fence_after();
+                        }
+                    }
                     const int row_t = m0 + (CG == 2 ? mt * 256 + static_cast<int>(rank) * 128 : mt * 128) + wq * 32;
                     uint32_t o[32];
                     {
