@@ -157,8 +157,8 @@ int b2q_reduce_partials(const float* partial, int splits, int64_t n, float scale
 
 /* Tuning hook: tile configuration of the two main kernels (0: 1 CTA, 128x128; 1: 1 CTA, 256x128;
  * 2: CTA pair, 256x256; 3: CTA pair, 512x256, direct epilogue stores; 4: as 3 with a TMA-store epilogue;
- * 5: as 3 with a warp-transposed, coalesced-store epilogue [default]; 6: experiment, as 5 with the UMMA issuer running
- * the first k-blocks of sub-tile 0 ahead while the epilogue still drains sub-tile 1 of the previous tile -- bit-identical
+ * 5: as 3 with a warp-transposed, coalesced-store epilogue [default]; 6: experiment, as 5 with the UMMA issue order
+ * rearranged at tile boundaries so that draining one 128-row sub-tile overlaps MMAs of the other -- bit-identical
  * results, not yet timed on hardware); -1 keeps the default / B2Q_*_VARIANT env. */
 int b2q_set_variant(int fwd_variant, int dx_variant);
 
