@@ -104,8 +104,11 @@ int b2q_dropout_bwd_add(void* dx_bf16, const void* dxl_bf16, int64_t n, uint64_t
 
 /* ---- QLoRA linear: tcgen05 / TMEM / TMA kernels ----------------------------------------- *
  * Shapes: x [M,K], W [N,K] (NF4), lora_A [r,K], lora_B [N,r], y / dy [M,N], u / du [M,r], all bf16
- * unless noted.  Contract: K % 64 == 0, N % 64 == 0, r in {16,32,64,128,256} and r % 16 == 0
- * for the LoRA operands (r % 64 == 0 for the fused tails), 16-byte aligned rows.           */
+ * unless noted.  Contract (anything else returns B2Q_ERR_SHAPE -- there is no slow path): r in {64, 128};
+ * b2q_qlora_fwd K % 64 == 0 and N % 256 == 0; b2q_qlora_bwd_dx N % 64 == 0 and K % 256 == 0; b2q_lora_grads
+ * K % 128 == 0 and N % 128 == 0; b2q_lora_down K % 64 == 0; b2q_lora_bwd_du N % 64 == 0; any M >= 1 (ragged tiles
+ * are handled); 16-byte aligned, contiguous rows.  Every LLaMA / Mistral / CLIP-L projection satisfies this.
+ * examples/c_host_example.c drives one forward + backward through these entry points from plain C. */
 
 /* u = drop(x) @ lora_A^T  (fp32 accumulate -> bf16);  us = bf16(scale * u) when us != NULL.
  * drop(x) = x * keep(seed, i) / (1 - drop_p), applied to the x tile in shared memory (no masked copy

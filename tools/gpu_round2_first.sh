@@ -11,6 +11,7 @@ step "smoke" 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out
 B2Q_EXPERIMENTAL=1 step "variant 6 parity" 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "variant6 or linear_fwd_bwd" > gpurun_out/r2_v6_parity.log 2>&1; tail -2 gpurun_out/r2_v6_parity.log
 B2Q_GEMV_CFG=3 step "tensor-core GEMV parity" 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k gemv > gpurun_out/r2_gemv3_parity.log 2>&1; tail -2 gpurun_out/r2_gemv3_parity.log
 B2Q_DX_MASK_FIRST=1 step "mask-first dX parity" 300 python -m pytest tests -m gpu -x -q -k "dropout or hf or mlp" > gpurun_out/r2_maskfirst_parity.log 2>&1; tail -2 gpurun_out/r2_maskfirst_parity.log
+B2Q_EXPERIMENTAL=1 step "plain-C host example" 200 python -m pytest tests/test_gpu_c_host.py -m gpu -x -q > gpurun_out/r2_c_host.log 2>&1; tail -2 gpurun_out/r2_c_host.log
 for cfg in 1 3; do B2Q_GEMV_CFG=$cfg step "GEMV timing cfg=$cfg" 200 python tests/gpu_gemv_bench.py > gpurun_out/r2_gemv_cfg$cfg.jsonl 2> gpurun_out/r2_gemv_cfg$cfg.err; tail -3 gpurun_out/r2_gemv_cfg$cfg.jsonl; done
 rm -f gpurun_out/sustained_bench.jsonl
 step "sustained kernels, variants 5 vs 6" 600 python tests/gpu_sustained_bench.py --variants 5,6 > gpurun_out/r2_sb_v56.log 2>&1; cp gpurun_out/sustained_bench.jsonl gpurun_out/r2_sb_v56.jsonl 2>/dev/null
