@@ -211,3 +211,31 @@ def test_dropout_mask_golden_fixture():
         assert int(m.sum()) == c["kept"]
         assert np.packbits(m.reshape(c["shape"])[0][:64]).tobytes().hex() == c["first_row_hex"]
         assert hashlib.sha256(np.packbits(m).tobytes()).hexdigest() == c["sha256"]
+
+
+def test_quantise_properties_over_random_scales():
+    """Property tests (hypothesis): for weights of any scale, (i) the decode error is bounded by the largest half-gap of
+    the code book times the block's absmax, (ii) re-quantising the fp32 decode reproduces the same codes and absmax
+    (the code book contains +-1, so absmax survives), (iii) the entry that set the absmax decodes to +-absmax exactly."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 2**31 - 1), st.floats(-18.0, 6.0), st.integers(1, 6))
+    def check(seed, log10_scale, nblocks):
+        rng = np.random.default_rng(seed)
+        w = (rng.standard_normal(64 * nblocks) * 10.0 ** log10_scale).astype(np.float32)
+        stq = nf4.quantize_nf4(w, 64, False)
+        dec = nf4.dequantize_nf4_f32(stq).reshape(-1)
+        am = np.repeat(stq["absmax"], 64)
+        half_gap = 0.5 * float(np.max(np.diff(nf4.NF4_CODE)))
+        # fl32 rounding of w * (1/absmax) can move a value across a threshold by one ulp: allow a few ulps of slack
+        assert np.all(np.abs(dec - w) <= am * (half_gap + 1e-6))
+        st2 = nf4.quantize_nf4(dec, 64, False)
+        assert np.array_equal(st2["packed"], stq["packed"]) and np.array_equal(st2["absmax"], stq["absmax"])
+        blocks = w.reshape(nblocks, 64)
+        idx = np.argmax(np.abs(blocks), axis=1)
+        peak = dec.reshape(nblocks, 64)[np.arange(nblocks), idx]
+        assert np.array_equal(np.abs(peak), stq["absmax"])
+
+    check()
