@@ -9,6 +9,7 @@ tensor is an error, not a fallback.
 from __future__ import annotations
 
 import ctypes as ct
+import functools
 from typing import Optional
 
 import torch
@@ -73,6 +74,18 @@ def _need_cuda(*tensors):
         if t.device.index != cur:
             raise RuntimeError(f"tensor on {t.device} but the current CUDA device is cuda:{cur}: wrap the call in "
                                "`with torch.cuda.device(tensor.device):`")
+
+
+def _on_device_of_first_arg(fn):
+    """bitsandbytes' ``pre_call(A.device)`` / ``post_call`` for the functions that mirror its public API: run on the device
+    of the first tensor even when that is not the calling thread's current device."""
+    @functools.wraps(fn)
+    def wrapper(A, *args, **kwargs):
+        if isinstance(A, torch.Tensor) and A.is_cuda and A.device.index != torch.cuda.current_device():
+            with torch.cuda.device(A.device):
+                return fn(A, *args, **kwargs)
+        return fn(A, *args, **kwargs)
+    return wrapper
 
 
 def _need(t: torch.Tensor, dtype, name: str):
@@ -185,6 +198,7 @@ class QuantState:
         return w
 
 
+@_on_device_of_first_arg
 def quantize_4bit(A: torch.Tensor, blocksize: int = 64, compress_statistics: bool = False, quant_type: str = "nf4",
                   quant_storage=torch.uint8):
     """NF4 blockwise quantisation on the GPU.  Returns (packed uint8 [(n+1)//2, 1], QuantState).
@@ -219,6 +233,7 @@ def quantize_4bit(A: torch.Tensor, blocksize: int = 64, compress_statistics: boo
     return packed, QuantState(absmax_q, A.shape, code, 64, "nf4", A.dtype, offset=offset, state2=state2)
 
 
+@_on_device_of_first_arg
 def dequantize_4bit(A: torch.Tensor, quant_state: QuantState, algo: int = 1) -> torch.Tensor:
     """Decode packed NF4 to a bf16 tensor of ``quant_state.shape`` (bit-exact with the reference decode).
 
@@ -239,6 +254,7 @@ def dequantize_4bit(A: torch.Tensor, quant_state: QuantState, algo: int = 1) -> 
 GEMV_MAX_ROWS = 8
 
 
+@_on_device_of_first_arg
 def gemv_4bit(x: torch.Tensor, packed: torch.Tensor, qs: QuantState) -> torch.Tensor:
     """y = x @ dequant(W)^T for up to 8 token rows (inference / `generate`): HBM-bound SIMT kernel, no tensor cores.
     Stand-in for ``bitsandbytes.functional.gemv_4bit``."""
@@ -259,6 +275,7 @@ def gemv_4bit(x: torch.Tensor, packed: torch.Tensor, qs: QuantState) -> torch.Te
 # ------------------------------------------------------------------------------ dropout ----
 def dropout_mask(shape, seed: int, p: float, device) -> torch.Tensor:
     mask = torch.empty(shape, dtype=torch.uint8, device=device)
+    _need_cuda(mask)
     _lib.check(_lib.load().b2q_dropout_mask(_p(mask), mask.numel(), seed, p, _stream()), "b2q_dropout_mask")
     return mask
 
