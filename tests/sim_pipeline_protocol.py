@@ -1,0 +1,226 @@
+"""Discrete-event model of the main kernels' barrier protocol (qlora_gemm.cuh): operand ring, UMMA issuer, asynchronous
+tensor pipe with tcgen05.commit semantics, epilogue -- for the default issue order (RA = 0) and the reordered one of
+variant 6 (RA = 3).  The roles are hand-ported from the kernel with the SAME index / phase arithmetic (stage `s`, phase
+bit `ph`, the `(s2 < s) ? ph ^ 1 : ph` look-ahead, accumulator phase `aph`); a random scheduler interleaves them and the
+model checks, over many seeds and shapes:
+
+  * no deadlock (every role runs to completion),
+  * every parity wait is satisfied by exactly the phase it meant (no aliasing: the barrier is never a phase ahead),
+  * an MMA reads the operand stage that holds ITS k-block of ITS tile,
+  * the accumulator sub-tile an MMA writes has been drained of the previous tile, and the epilogue drains a sub-tile
+    only after all of its MMAs have executed.
+
+Pure Python, no GPU: a design check, run by tests/test_host.py.  It does not model TMA, decode or TMEM timing.
+"""
+import random
+
+STAGES = 4
+MT = 2
+
+
+class Bar:
+    def __init__(self, count):
+        self.count, self.pending, self.completed = count, count, 0   # completed = number of finished phases
+
+    def arrive(self):
+        self.pending -= 1
+        assert self.pending >= 0, "more arrivals than the barrier expects"
+        if self.pending == 0:
+            self.pending = self.count
+            self.completed += 1
+
+    def passes(self, parity):
+        return (self.completed & 1) != parity   # try_wait.parity: the phase with this parity has completed
+
+
+class Deadlock(Exception):
+    pass
+
+
+def simulate(num_tiles, kb_total, ra_cfg, seed):
+    rng = random.Random(seed)
+    full = [Bar(2) for _ in range(STAGES)]      # producer + decode group
+    empty = [Bar(1) for _ in range(STAGES)]     # tcgen05.commit
+    tfull, tfull1 = Bar(1), Bar(1)
+    tempty = [Bar(1) for _ in range(MT)]        # the epilogue as one agent
+    stage_content = [None] * STAGES             # (tile, kb) the producer / decode wrote
+    stage_ready = [0] * STAGES                  # writers done for the current content (2 = both)
+    pipe = []                                   # tensor-pipe FIFO: ("mma", tile, kb, mt, stage) | ("commit", bar)
+    acc_mmas = {}                               # (tile, mt) -> executed k-blocks
+    acc_drained = {(-1, 0): True, (-1, 1): True}
+    log = {"waits": 0, "issuer_done": False}
+
+    def wait(bar, parity, intended):
+        """Generator: block until the barrier's phase `intended` (0-based) has completed, via the parity the kernel uses."""
+        while not bar.passes(parity):
+            yield "blocked"
+        log["waits"] += 1
+        assert bar.completed == intended + 1, f"parity alias: wanted phase {intended}, barrier completed {bar.completed}"
+
+    def writer(which):   # which = 0 producer (TMA), 1 decode group: both wait for the slot, fill it, arrive on full
+        s, ph, use = 0, 0, [0] * STAGES
+        for tile in range(num_tiles):
+            for kb in range(kb_total):
+                yield from wait(empty[s], ph ^ 1, use[s] - 1) if use[s] > 0 else iter(())
+                if use[s] == 0:
+                    assert empty[s].passes(ph ^ 1)          # fresh barrier: the kernel's first wait passes immediately
+                if which == 0:
+                    stage_content[s] = (tile, kb)
+                stage_ready[s] += 1
+                yield "step"
+                full[s].arrive()
+                use[s] += 1
+                s += 1
+                if s == STAGES:
+                    s, ph = 0, ph ^ 1
+
+    def issuer():
+        s, ph, aph = 0, 0, 0
+        use = [0] * STAGES                      # completed uses of each stage so far (for the intended-phase check)
+
+        def issue(stage, mt, tile, kb):
+            pipe.append(("mma", tile, kb, mt, stage))
+
+        for tile in range(num_tiles):
+            if ra_cfg == 0:
+                for kb in range(kb_total):
+                    yield from wait(full[s], ph, use[s])
+                    for mt in range(MT):
+                        if kb == 0:
+                            yield from wait(tempty[mt], aph ^ 1, tile - 1) if tile > 0 else iter(())
+                        issue(s, mt, tile, kb)
+                        yield "step"
+                    pipe.append(("commit", empty[s]))
+                    if kb == kb_total - 1:
+                        pipe.append(("commit", tfull))
+                    use[s] += 1
+                    s += 1
+                    if s == STAGES:
+                        s, ph = 0, ph ^ 1
+            else:
+                ra = min(kb_total, ra_cfg)
+                rt = min(kb_total - ra, ra_cfg)
+                # head
+                if tile > 0:
+                    yield from wait(tempty[0], aph ^ 1, tile - 1)
+                s2 = s
+                look = {}
+                for kb in range(ra):
+                    yield from wait(full[s2], (ph ^ 1) if s2 < s else ph, use[s2])
+                    look[kb] = s2
+                    issue(s2, 0, tile, kb)
+                    if kb == kb_total - 1:
+                        pipe.append(("commit", tfull))
+                    yield "step"
+                    s2 = (s2 + 1) % STAGES
+                if tile > 0:
+                    yield from wait(tempty[1], aph ^ 1, tile - 1)
+                for kb in range(ra):
+                    assert look[kb] == s
+                    issue(s, 1, tile, kb)
+                    pipe.append(("commit", empty[s]))
+                    if kb == kb_total - 1:
+                        pipe.append(("commit", tfull1))
+                    use[s] += 1
+                    yield "step"
+                    s += 1
+                    if s == STAGES:
+                        s, ph = 0, ph ^ 1
+                kb_end = kb_total - rt
+                for kb in range(ra, kb_end):
+                    yield from wait(full[s], ph, use[s])
+                    for mt in range(MT):
+                        issue(s, mt, tile, kb)
+                        if mt == 0 and kb == kb_total - 1:
+                            pipe.append(("commit", tfull))
+                        yield "step"
+                    pipe.append(("commit", empty[s]))
+                    if kb == kb_total - 1:
+                        pipe.append(("commit", tfull1))
+                    use[s] += 1
+                    s += 1
+                    if s == STAGES:
+                        s, ph = 0, ph ^ 1
+                if rt > 0:
+                    s2 = s
+                    for kb in range(kb_end, kb_total):
+                        yield from wait(full[s2], (ph ^ 1) if s2 < s else ph, use[s2])
+                        issue(s2, 0, tile, kb)
+                        yield "step"
+                        s2 = (s2 + 1) % STAGES
+                    pipe.append(("commit", tfull))
+                    for kb in range(kb_end, kb_total):
+                        issue(s, 1, tile, kb)
+                        pipe.append(("commit", empty[s]))
+                        use[s] += 1
+                        yield "step"
+                        s += 1
+                        if s == STAGES:
+                            s, ph = 0, ph ^ 1
+                    pipe.append(("commit", tfull1))
+            aph ^= 1
+        log["issuer_done"] = True
+
+    def epilogue():
+        aph = 0
+        for tile in range(num_tiles):
+            yield from wait(tfull, aph, tile)
+            for mt in range(MT):
+                if ra_cfg > 0 and mt == 1:
+                    yield from wait(tfull1, aph, tile)
+                assert acc_mmas.get((tile, mt), 0) == kb_total, f"drain of tile {tile} sub-tile {mt} before its MMAs finished"
+                yield "step"                      # the drain itself takes time
+                acc_drained[(tile, mt)] = True
+                tempty[mt].arrive()
+            aph ^= 1
+
+    def tensor_pipe():
+        done = 0
+        total = num_tiles * kb_total * MT
+        while not log["issuer_done"] or pipe:
+            if not pipe:
+                yield "blocked"
+                continue
+            op = pipe.pop(0)
+            if op[0] == "commit":
+                op[1].arrive()                     # all earlier MMAs have executed (FIFO)
+            else:
+                _, tile, kb, mt, stage = op
+                assert stage_content[stage] == (tile, kb), f"MMA of tile {tile} kb {kb} read stage holding {stage_content[stage]}"
+                assert acc_drained.get((tile - 1, mt), False), f"MMA into sub-tile {mt} of tile {tile} before tile {tile - 1} was drained"
+                assert acc_mmas.get((tile, mt), 0) == kb, "k-blocks of one accumulator out of order"
+                acc_mmas[(tile, mt)] = kb + 1
+                done += 1
+            yield "step"
+        assert done == total
+
+    agents = {"producer": writer(0), "decode": writer(1), "issuer": issuer(), "epilogue": epilogue(), "pipe": tensor_pipe()}
+    blocked_rounds = 0
+    while agents:
+        name = rng.choice(sorted(agents))
+        try:
+            r = next(agents[name])
+        except StopIteration:
+            del agents[name]
+            blocked_rounds = 0
+            continue
+        blocked_rounds = blocked_rounds + 1 if r == "blocked" else 0
+        if blocked_rounds > 20000:
+            raise Deadlock(f"roles still alive: {sorted(agents)} (tiles {num_tiles}, kb {kb_total}, RA {ra_cfg}, seed {seed})")
+    assert all(acc_drained.get((t, m)) for t in range(num_tiles) for m in range(MT))
+    return log["waits"]
+
+
+def run_all(seeds=12):
+    n = 0
+    for ra in (0, 3):
+        for kb_total in (1, 2, 3, 4, 5, 6, 7, 9, 17):
+            for tiles in (1, 2, 3, 5):
+                for seed in range(seeds):
+                    simulate(tiles, kb_total, ra, seed)
+                    n += 1
+    return n
+
+
+if __name__ == "__main__":
+    print("configurations simulated without deadlock or hazard:", run_all())

@@ -186,3 +186,16 @@ def test_bench_control_flow_dry_run(extra):
         assert d["e2e"]["api"].startswith("C-ABI") and "did not finish" in d["note"] and d["value"] > 0
     else:
         assert "dry run OK" in r.stdout
+
+
+def test_pipeline_protocol_model():
+    """tests/sim_pipeline_protocol.py: the operand-ring / accumulator barrier protocol of the main kernels, default and
+    variant-6 issue order, runs to completion under random interleavings with no phase aliasing and no operand or
+    accumulator hazard."""
+    import importlib.util
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sim_pipeline_protocol.py")
+    spec = importlib.util.spec_from_file_location("sim_pipeline_protocol", path)
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    assert sim.run_all(seeds=6) == 2 * 9 * 4 * 6
