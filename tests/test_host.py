@@ -199,3 +199,20 @@ def test_pipeline_protocol_model():
     sim = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(sim)
     assert sim.run_all(seeds=6) == 2 * 9 * 4 * 6
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) runs without a GPU and prints the JSON contract."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["impl"] == "reference" and d["metric"] == "qlora_linear_stack_train_tokens_per_s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] and d["higher_is_better"] is True and d["vs_baseline"] is None
