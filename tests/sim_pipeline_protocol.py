@@ -211,6 +211,101 @@ def simulate(num_tiles, kb_total, ra_cfg, seed):
     return log["waits"]
 
 
+def simulate_two_sets(num_tiles, kb_total, seed, stages=5):
+    """The masked dX GEMM (GemmKNMask): MT = 1, double-buffered accumulator, TWO epilogue warp sets -- set e drains the
+    tiles whose sequence number is e (mod 2) from accumulator stage e, with its own phase bit."""
+    rng = random.Random(seed)
+    full = [Bar(1) for _ in range(stages)]      # TMA producer only (both operands by TMA)
+    empty = [Bar(1) for _ in range(stages)]
+    tfull = [Bar(1), Bar(1)]
+    tempty = [Bar(1), Bar(1)]
+    stage_content = [None] * stages
+    pipe = []
+    acc_mmas, acc_drained = {}, {(-1, 0): True, (-2, 0): True}
+    log = {"issuer_done": False}
+
+    def wait(bar, parity, intended):
+        while not bar.passes(parity):
+            yield "blocked"
+        assert bar.completed == intended + 1, f"parity alias: wanted phase {intended}, barrier completed {bar.completed}"
+
+    def producer():
+        s, ph, use = 0, 0, [0] * stages
+        for tile in range(num_tiles):
+            for kb in range(kb_total):
+                if use[s] > 0:
+                    yield from wait(empty[s], ph ^ 1, use[s] - 1)
+                stage_content[s] = (tile, kb)
+                yield "step"
+                full[s].arrive()
+                use[s] += 1
+                s += 1
+                if s == stages:
+                    s, ph = 0, ph ^ 1
+
+    def issuer():
+        s, ph, acc, aph, use = 0, 0, 0, 0, [0] * stages
+        for tile in range(num_tiles):
+            for kb in range(kb_total):
+                yield from wait(full[s], ph, use[s])
+                if kb == 0 and tile >= 2:
+                    yield from wait(tempty[acc], aph ^ 1, tile // 2 - 1)
+                pipe.append(("mma", tile, kb, acc, s))
+                yield "step"
+                pipe.append(("commit", empty[s]))
+                if kb == kb_total - 1:
+                    pipe.append(("commit", tfull[acc]))
+                use[s] += 1
+                s += 1
+                if s == stages:
+                    s, ph = 0, ph ^ 1
+            acc += 1
+            if acc == 2:
+                acc, aph = 0, aph ^ 1
+        log["issuer_done"] = True
+
+    def epilogue(eset):
+        aph = 0
+        for n, tile in enumerate(range(eset, num_tiles, 2)):
+            yield from wait(tfull[eset], aph, n)
+            assert acc_mmas.get(tile, 0) == kb_total, f"set {eset} drains tile {tile} before its MMAs finished"
+            yield "step"
+            acc_drained[(tile, 0)] = True
+            tempty[eset].arrive()
+            aph ^= 1
+
+    def tensor_pipe():
+        while not log["issuer_done"] or pipe:
+            if not pipe:
+                yield "blocked"
+                continue
+            op = pipe.pop(0)
+            if op[0] == "commit":
+                op[1].arrive()
+            else:
+                _, tile, kb, acc, stage = op
+                assert stage_content[stage] == (tile, kb), f"MMA of tile {tile} kb {kb} read stage holding {stage_content[stage]}"
+                assert acc_drained.get((tile - 2, 0), False), f"MMA into accumulator stage {acc} of tile {tile} before tile {tile - 2} was drained"
+                assert acc_mmas.get(tile, 0) == kb
+                acc_mmas[tile] = kb + 1
+            yield "step"
+
+    agents = {"producer": producer(), "issuer": issuer(), "epi0": epilogue(0), "epi1": epilogue(1), "pipe": tensor_pipe()}
+    blocked_rounds = 0
+    while agents:
+        name = rng.choice(sorted(agents))
+        try:
+            r = next(agents[name])
+        except StopIteration:
+            del agents[name]
+            blocked_rounds = 0
+            continue
+        blocked_rounds = blocked_rounds + 1 if r == "blocked" else 0
+        if blocked_rounds > 20000:
+            raise Deadlock(f"roles still alive: {sorted(agents)} (two sets, tiles {num_tiles}, kb {kb_total}, seed {seed})")
+    assert all(acc_drained.get((t, 0)) for t in range(num_tiles))
+
+
 def run_all(seeds=12):
     n = 0
     for ra in (0, 3):
@@ -219,6 +314,10 @@ def run_all(seeds=12):
                 for seed in range(seeds):
                     simulate(tiles, kb_total, ra, seed)
                     n += 1
+    for kb_total in (1, 2, 3):
+        for tiles in (1, 2, 3, 4, 7):
+            for seed in range(seeds):
+                simulate_two_sets(tiles, kb_total, seed)
     return n
 
 
