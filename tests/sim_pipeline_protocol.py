@@ -306,6 +306,97 @@ def simulate_two_sets(num_tiles, kb_total, seed, stages=5):
     assert all(acc_drained.get((t, 0)) for t in range(num_tiles))
 
 
+def simulate_transform(num_tiles, kb_total, seed, stages=6, groups=4):
+    """The A-operand transform kernels (LoRA dropout in shared memory): `groups` transform groups take ring positions in
+    turn (position si belongs to group si % groups), wait for the TMA data with the parity of (si / stages), mask the
+    tile in place and arrive on the stage's "transformed" barrier, which is what the UMMA issuer waits for."""
+    rng = random.Random(seed)
+    full = [Bar(1) for _ in range(stages)]
+    xf = [Bar(1) for _ in range(stages)]        # one arrive per warp of the owning group (modelled as one)
+    empty = [Bar(1) for _ in range(stages)]
+    stage_content, stage_masked = [None] * stages, [False] * stages
+    pipe = []
+    log = {"issuer_done": False, "mmas": 0}
+
+    def wait(bar, parity, intended):
+        while not bar.passes(parity):
+            yield "blocked"
+        assert bar.completed == intended + 1, f"parity alias: wanted phase {intended}, barrier completed {bar.completed}"
+
+    def producer():
+        s, ph, use = 0, 0, [0] * stages
+        for tile in range(num_tiles):
+            for kb in range(kb_total):
+                if use[s] > 0:
+                    yield from wait(empty[s], ph ^ 1, use[s] - 1)
+                stage_content[s], stage_masked[s] = (tile, kb), False
+                yield "step"
+                full[s].arrive()
+                use[s] += 1
+                s += 1
+                if s == stages:
+                    s, ph = 0, ph ^ 1
+
+    def group(g):
+        it = 0
+        for tile in range(num_tiles):
+            kb = (g - it) & (groups - 1)
+            while kb < kb_total:
+                si = it + kb
+                st, ph = si % stages, (si // stages) & 1
+                yield from wait(full[st], ph, si // stages)
+                assert stage_content[st] == (tile, kb) and not stage_masked[st]
+                yield "step"
+                stage_masked[st] = True
+                xf[st].arrive()
+                kb += groups
+            it += kb_total
+
+    def issuer():
+        s, ph, use = 0, 0, [0] * stages
+        for tile in range(num_tiles):
+            for kb in range(kb_total):
+                yield from wait(xf[s], ph, use[s])
+                pipe.append(("mma", tile, kb, s))
+                yield "step"
+                pipe.append(("commit", empty[s]))
+                use[s] += 1
+                s += 1
+                if s == stages:
+                    s, ph = 0, ph ^ 1
+        log["issuer_done"] = True
+
+    def tensor_pipe():
+        while not log["issuer_done"] or pipe:
+            if not pipe:
+                yield "blocked"
+                continue
+            op = pipe.pop(0)
+            if op[0] == "commit":
+                op[1].arrive()
+            else:
+                _, tile, kb, st = op
+                assert stage_content[st] == (tile, kb) and stage_masked[st], "MMA read an unmasked or overwritten stage"
+                log["mmas"] += 1
+            yield "step"
+
+    agents = {"producer": producer(), "issuer": issuer(), "pipe": tensor_pipe()}
+    agents.update({f"xf{g}": group(g) for g in range(groups)})
+    blocked_rounds = 0
+    while agents:
+        name = rng.choice(sorted(agents))
+        try:
+            r = next(agents[name])
+        except StopIteration:
+            del agents[name]
+            blocked_rounds = 0
+            continue
+        blocked_rounds = blocked_rounds + 1 if r == "blocked" else 0
+        if blocked_rounds > 40000:
+            raise Deadlock(f"roles still alive: {sorted(agents)} (transform, tiles {num_tiles}, kb {kb_total}, seed {seed})")
+    assert log["mmas"] == num_tiles * kb_total
+
+
 def run_all(seeds=12):
     n = 0
     for ra in (0, 3):
@@ -318,6 +409,10 @@ def run_all(seeds=12):
         for tiles in (1, 2, 3, 4, 7):
             for seed in range(seeds):
                 simulate_two_sets(tiles, kb_total, seed)
+    for kb_total in (1, 2, 3, 5, 6, 7, 13, 64):
+        for tiles in (1, 2, 3):
+            for seed in range(max(1, seeds // 3)):
+                simulate_transform(tiles, kb_total, seed)
     return n
 
 
