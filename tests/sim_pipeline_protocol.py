@@ -397,6 +397,132 @@ def simulate_transform(num_tiles, kb_total, seed, stages=6, groups=4):
     assert log["mmas"] == num_tiles * kb_total
 
 
+def simulate_decode(num_tiles, kb_main, kb_tail, seed, stages=4, pst=4, ng=2):
+    """The decode kernels' main loop: operand ring (A by TMA; B decoded for main k-blocks, by TMA for the LoRA tail
+    k-blocks), an independent packed-NF4 ring of depth `pst`, and `ng` decode groups -- group g owns the operand-ring
+    positions si with si % ng == g, reads packed position pi = (main k-blocks so far) and releases it, waits for the
+    operand slot, writes the decoded tile and arrives on the stage's full barrier; for tail k-blocks the owner only
+    arrives."""
+    rng = random.Random(seed)
+    kb_total = kb_main + kb_tail
+    full = [Bar(2) for _ in range(stages)]      # TMA producer + the owning decode group
+    empty = [Bar(1) for _ in range(stages)]
+    pk = [Bar(1) for _ in range(pst)]
+    pk_empty = [Bar(1) for _ in range(pst)]
+    a_content, b_content, p_content = [None] * stages, [None] * stages, [None] * pst
+    pipe = []
+    log = {"issuer_done": False, "mmas": 0}
+
+    def wait(bar, parity, intended):
+        while not bar.passes(parity):
+            yield "blocked"
+        assert bar.completed == intended + 1, f"parity alias: wanted phase {intended}, barrier completed {bar.completed}"
+
+    def producer():
+        s, ph, use = 0, 0, [0] * stages
+        for tile in range(num_tiles):
+            for kb in range(kb_total):
+                if use[s] > 0:
+                    yield from wait(empty[s], ph ^ 1, use[s] - 1)
+                a_content[s] = (tile, kb)
+                if kb >= kb_main:
+                    b_content[s] = (tile, kb)      # tail: B by TMA
+                yield "step"
+                full[s].arrive()
+                use[s] += 1
+                s += 1
+                if s == stages:
+                    s, ph = 0, ph ^ 1
+
+    def packed_producer():
+        ps, pph, use = 0, 0, [0] * pst
+        for tile in range(num_tiles):
+            for kb in range(kb_main):
+                if use[ps] > 0:
+                    yield from wait(pk_empty[ps], pph ^ 1, use[ps] - 1)
+                p_content[ps] = (tile, kb)
+                yield "step"
+                pk[ps].arrive()
+                use[ps] += 1
+                ps += 1
+                if ps == pst:
+                    ps, pph = 0, pph ^ 1
+
+    def group(g):
+        it = pit = 0
+        for tile in range(num_tiles):
+            kb = (g - it) & (ng - 1)
+            while kb < kb_main:
+                pi = pit + kb
+                ps, pph = pi % pst, (pi // pst) & 1
+                yield from wait(pk[ps], pph, pi // pst)
+                assert p_content[ps] == (tile, kb), "decode read a packed slot holding another k-block"
+                yield "step"
+                pk_empty[ps].arrive()
+                si = it + kb
+                st, ph = si % stages, (si // stages) & 1
+                if si >= stages:
+                    yield from wait(empty[st], ph ^ 1, si // stages - 1)
+                b_content[st] = (tile, kb)
+                yield "step"
+                full[st].arrive()
+                kb += ng
+            for kb in range(kb_main, kb_total):
+                si = it + kb
+                if (si & (ng - 1)) != g:
+                    continue
+                st, ph = si % stages, (si // stages) & 1
+                if si >= stages:
+                    yield from wait(empty[st], ph ^ 1, si // stages - 1)
+                full[st].arrive()
+            it += kb_total
+            pit += kb_main
+
+    def issuer():
+        s, ph, use = 0, 0, [0] * stages
+        for tile in range(num_tiles):
+            for kb in range(kb_total):
+                yield from wait(full[s], ph, use[s])
+                pipe.append(("mma", tile, kb, s))
+                yield "step"
+                pipe.append(("commit", empty[s]))
+                use[s] += 1
+                s += 1
+                if s == stages:
+                    s, ph = 0, ph ^ 1
+        log["issuer_done"] = True
+
+    def tensor_pipe():
+        while not log["issuer_done"] or pipe:
+            if not pipe:
+                yield "blocked"
+                continue
+            op = pipe.pop(0)
+            if op[0] == "commit":
+                op[1].arrive()
+            else:
+                _, tile, kb, st = op
+                assert a_content[st] == (tile, kb) and b_content[st] == (tile, kb), "MMA read a stage holding other data"
+                log["mmas"] += 1
+            yield "step"
+
+    agents = {"producer": producer(), "packed": packed_producer(), "issuer": issuer(), "pipe": tensor_pipe()}
+    agents.update({f"dec{g}": group(g) for g in range(ng)})
+    blocked_rounds = 0
+    while agents:
+        name = rng.choice(sorted(agents))
+        try:
+            r = next(agents[name])
+        except StopIteration:
+            del agents[name]
+            blocked_rounds = 0
+            continue
+        blocked_rounds = blocked_rounds + 1 if r == "blocked" else 0
+        if blocked_rounds > 40000:
+            raise Deadlock(f"roles still alive: {sorted(agents)} (decode, tiles {num_tiles}, kb {kb_main}+{kb_tail}, seed {seed})")
+    assert log["mmas"] == num_tiles * kb_total
+
+
 def run_all(seeds=12):
     n = 0
     for ra in (0, 3):
@@ -413,6 +539,11 @@ def run_all(seeds=12):
         for tiles in (1, 2, 3):
             for seed in range(max(1, seeds // 3)):
                 simulate_transform(tiles, kb_total, seed)
+    for kb_main in (1, 2, 4, 5, 8, 16, 64):
+        for kb_tail in (0, 1, 2):
+            for tiles in (1, 2, 3, 5):
+                for seed in range(max(1, seeds // 3)):
+                    simulate_decode(tiles, kb_main, kb_tail, seed)
     return n
 
 
