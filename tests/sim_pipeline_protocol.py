@@ -10,6 +10,11 @@ model checks, over many seeds and shapes:
   * the accumulator sub-tile an MMA writes has been drained of the previous tile, and the epilogue drains a sub-tile
     only after all of its MMAs have executed.
 
+Also modelled, with the same checks: the double-buffered, two-epilogue-set variant (masked dX GEMM), the transform-group
+ring of the LoRA-dropout kernels (4 groups over a 6-stage ring), and the decode kernels' operand + packed rings with two
+decode groups and LoRA tail k-blocks (the `it` / `pit` position arithmetic).  Each model is mutation-checked: breaking
+the phase look-ahead, the packed-ring position, the tail ownership or the sub-tile-1 wait makes it fail.
+
 Pure Python, no GPU: a design check, run by tests/test_host.py.  It does not model TMA, decode or TMEM timing.
 """
 import random
