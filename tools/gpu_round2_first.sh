@@ -15,6 +15,7 @@ B2Q_EXPERIMENTAL=1 step "plain-C host example" 200 python -m pytest tests/test_g
 for cfg in 1 3; do B2Q_GEMV_CFG=$cfg step "GEMV timing cfg=$cfg" 200 python tests/gpu_gemv_bench.py > gpurun_out/r2_gemv_cfg$cfg.jsonl 2> gpurun_out/r2_gemv_cfg$cfg.err; tail -3 gpurun_out/r2_gemv_cfg$cfg.jsonl; done
 rm -f gpurun_out/sustained_bench.jsonl
 step "sustained kernels, variants 5 vs 6" 600 python tests/gpu_sustained_bench.py --variants 5,6 > gpurun_out/r2_sb_v56.log 2>&1; cp gpurun_out/sustained_bench.jsonl gpurun_out/r2_sb_v56.jsonl 2>/dev/null
+for v in 5 6; do step "phase trace fwd variant $v" 200 python tests/gpu_trace.py fwd $v > gpurun_out/r2_trace_fwd_v$v.log 2>&1; done
 step "bench (default)" 600 python bench.py --no-cpu > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 B2Q_FWD_VARIANT=6 B2Q_DX_VARIANT=6 step "bench (variant 6)" 600 python bench.py --no-cpu --no-opt > gpurun_out/r2_bench_v6.json 2> gpurun_out/r2_bench_v6.err
 B2Q_DX_MASK_FIRST=1 step "bench (mask-first dX)" 600 python bench.py --no-cpu --no-opt > gpurun_out/r2_bench_maskfirst.json 2> gpurun_out/r2_bench_maskfirst.err
