@@ -167,6 +167,8 @@ static long long* g_trace = nullptr;   // debug: phase trace buffer for the next
 static int g_trace_tiles = 0;
 static int g_pf_dist = 0;
 static int g_pdl = -1;   // -1: read B2Q_PDL (default off)
+static const uint8_t* g_mask_bits = nullptr;   // experiment: packed dropout mask for the next lora_down / lora_grads calls
+static long long g_mask_bytes = 0;
 
 template <class Cfg>
 static int launch(GemmParams& p, cudaStream_t stream) {
@@ -257,6 +259,9 @@ template <int R> constexpr int skinny_stages() { return 6; }
 template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>()>;   // u = x A^T
 template <int R> using DownDropCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>(), 0, 0, true>;   // u = drop(x) A^T
 template <int R> using GradADropCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true>;
+// experiment (b2q_debug_set_mask_bits): the same two kernels reading a packed mask instead of hashing it
+template <int R> using DownDropBitsCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>(), 0, 0, true, 0, 1, 0, true>;
+template <int R> using GradADropBitsCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true, 0, 1, 0, true>;
 // dx += keep * (du A) / (1 - p): masked epilogue, 128-bit vector reductions into dx at the L2 (dropout backward)
 using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 5, 0, 0, false, -1, 2>;   // two epilogue warp sets
 template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, skinny_stages<R>()>;      // du = s dy B
@@ -285,6 +290,12 @@ extern "C" const char* b2q_error_string(int code) {
         case B2Q_ERR_COMM: return "b2q: NCCL unavailable or an NCCL call failed";
         default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "b2q: unknown error";
     }
+}
+
+extern "C" int b2q_debug_set_mask_bits(const void* bits, int64_t bytes) {
+    g_mask_bits = static_cast<const uint8_t*>(bits);
+    g_mask_bytes = bits != nullptr ? static_cast<long long>(bytes) : 0;
+    return 0;
 }
 
 extern "C" int b2q_debug_set_trace(void* buf, int tiles_per_cta) {
@@ -430,6 +441,12 @@ static int lora_down_r(const void* x, const void* lora_A, float scale, uint64_t 
     int e;
     if ((e = map_bf16_kmajor(&p.tmA, x, M, K, 128))) return e;
     if ((e = map_bf16_kmajor(&p.tmB, lora_A, R, K, R))) return e;
+    if (drop_p > 0.f && g_mask_bits != nullptr) {
+        if (g_mask_bytes < static_cast<long long>(M) * K / 8 || g_mask_bytes >= (1ll << 32)) return B2Q_ERR_ARG;
+        p.mask_bits = g_mask_bits;
+        p.mask_bytes = g_mask_bytes;
+        return launch<DownDropBitsCfg<R>>(p, stream);
+    }
     if (drop_p > 0.f) return launch<DownDropCfg<R>>(p, stream);
     return launch<DownCfg<R>>(p, stream);
 }
@@ -493,7 +510,12 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
         p.seed = seed; p.thresh16 = dropout_threshold(drop_p); p.xf_ld = K;
         if ((e = map_bf16_mnmajor(&p.tmA, xd, M, K))) return e;
         if ((e = map_bf16_mnmajor(&p.tmB, du, M, R))) return e;
-        if (drop_p > 0.f) e = launch<GradADropCfg<R>>(p, stream); else e = launch<GradACfg<R>>(p, stream);
+        if (drop_p > 0.f && g_mask_bits != nullptr) {
+            if (g_mask_bytes < static_cast<long long>(M) * K / 8 || g_mask_bytes >= (1ll << 32)) return B2Q_ERR_ARG;
+            p.mask_bits = g_mask_bits;
+            p.mask_bytes = g_mask_bytes;
+            e = launch<GradADropBitsCfg<R>>(p, stream);
+        } else if (drop_p > 0.f) e = launch<GradADropCfg<R>>(p, stream); else e = launch<GradACfg<R>>(p, stream);
         if (e) return e;
         if ((e = b2q_reduce_partials(wa, sa, static_cast<int64_t>(R) * K, 1.0f / (1.0f - drop_p), dA, accumulate,
                                      stream)))

@@ -72,11 +72,17 @@ struct GemmParams {
     long long* trace;
     int trace_tiles;
     int pf_dist;       // L2 prefetch distance of the A operand in k-blocks (0 = off)
+    // experiment (XF_BITS configs): packed LoRA-dropout mask of the activation, bit k of byte b = keep(8 b + k)
+    const uint8_t* mask_bits;
+    long long mask_bytes;   // size of mask_bits (rows of the operand tile past the activation read nothing)
 };
 
 template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_, int NG_ = 2,
-          int PST_ = 6, bool A_XF_ = false, int STG_ = 0, int ESETS_ = 1, int RA_ = 0>
+          int PST_ = 6, bool A_XF_ = false, int STG_ = 0, int ESETS_ = 1, int RA_ = 0, bool XF_BITS_ = false>
 struct GemmCfg {
+    // XF_BITS (experiment): the A-operand transform reads the packed mask (GemmParams::mask_bits) instead of hashing.
+    static constexpr bool XF_BITS = XF_BITS_;
+    static_assert(!XF_BITS_ || A_XF_, "XF_BITS is a mode of the A-operand transform");
     // RA > 0 (experiment, MT == 2 with a single accumulator stage): the UMMA issuer reorders the first and the last RA
     // k-blocks of a tile.  Head: sub-tile 0 of the first RA k-blocks as soon as the epilogue has drained sub-tile 0 of the
     // previous tile, then sub-tile 1 of the same k-blocks (releasing their operand stages) once sub-tile 1 is drained
@@ -730,6 +736,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         const int t = (threadIdx.x - 256) % XT;
         const uint32_t seed_lo = static_cast<uint32_t>(p.seed), seed_hi = static_cast<uint32_t>(p.seed >> 32);
         const uint32_t thr = p.thresh16;
+        [[maybe_unused]] const uint32_t mask_bytes32 = static_cast<uint32_t>(p.mask_bytes);   // < 4 GB, checked by the host
         uint32_t it = 0;   // ring position over all k-blocks of all tiles
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
             int mt_i, nt_i, split;
@@ -739,7 +746,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             for (int kb = static_cast<int>((static_cast<uint32_t>(g) - it) & (XG - 1)); kb < kb_total; kb += XG) {
                 const int k0 = (kb0 + kb) * 64;
                 const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
-                mbar_wait(full_bar(s), ph);
+                if constexpr (!Cfg::XF_BITS) mbar_wait(full_bar(s), ph);
                 // hash counter of chunk i = counter of chunk 0 + a multiple of xf_ld (XT = 128: rows advance by 16 per chunk)
                 uint32_t j0_base;
                 {
@@ -749,6 +756,29 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     j0_base = static_cast<uint32_t>(static_cast<unsigned long long>(e_base) >> 2);
                 }
                 const uint32_t j0_step = static_cast<uint32_t>(p.xf_ld) * 4u;   // 16 rows further = 16 * xf_ld elements = 4 * xf_ld counters
+                if constexpr (Cfg::XF_BITS) {
+                    // mask bytes of this thread's eight chunks (byte index = element index / 8 = counter / 2): they depend
+                    // only on the position, so the loads are in flight while the thread waits for the operand tile
+                    uint32_t mb[1024 / XT];
+#pragma unroll
+                    for (int i = 0; i < 1024 / XT; ++i) {
+                        const uint32_t j0 = Cfg::A_MN ? j0_base + static_cast<uint32_t>(i & 3) * j0_step + static_cast<uint32_t>(i >> 2) * 16u
+                                                      : j0_base + static_cast<uint32_t>(i) * j0_step;
+                        const uint32_t bi = j0 >> 1;
+                        mb[i] = bi < mask_bytes32 ? static_cast<uint32_t>(__ldg(p.mask_bits + bi)) : 0xFFu;   // past the activation: zeros anyway
+                    }
+                    mbar_wait(full_bar(s), ph);
+#pragma unroll
+                    for (int i = 0; i < 1024 / XT; ++i) {
+                        const uint32_t addr = a_stage(s) + (t + XT * i) * 16;
+                        uint32_t w[4], m[4];
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+                        dropout_byte_to_masks(mb[i], m);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0] & m[0]), "r"(w[1] & m[1]),
+                                     "r"(w[2] & m[2]), "r"(w[3] & m[3]) : "memory");
+                    }
+                } else
 #pragma unroll
                 for (int i = 0; i < 1024 / XT; ++i) {
                     const int q = t + XT * i;

@@ -470,3 +470,37 @@ def test_experimental_variant6_bit_identical_to_default(F, cuda_dev):
         finally:
             F.set_variant(-1, -1)
     assert torch.equal(outs[5][0], outs[6][0]) and torch.equal(outs[5][1], outs[6][1])
+
+
+@pytest.mark.skipif(os.environ.get("B2Q_EXPERIMENTAL") != "1", reason="experiments not yet run on hardware (B2Q_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("M,K,r", [(512, 768, 64), (333, 1024, 128)])
+def test_experimental_mask_bits_path_is_bit_identical(F, cuda_dev, M, K, r):
+    """Packed-mask experiment: the bits equal the exported byte mask, and lora_down / lora_grads give the same bits
+    whether they hash the mask in shared memory or read the packed copy."""
+    seed, p, N = 4242, 0.05, 512
+    ref_mask = F.dropout_mask((M, K), seed, p, cuda_dev).cpu().numpy().reshape(-1)
+    if (M * K) % 32 == 0:
+        bits = F.dropout_mask_bits((M, K), seed, p, cuda_dev).cpu().numpy()
+        assert np.array_equal(np.unpackbits(bits, bitorder="little"), ref_mask)
+    gen = torch.Generator(device=cuda_dev).manual_seed(1)
+    x = torch.randn(M, K, device=cuda_dev, generator=gen).bfloat16()
+    dy = (torch.randn(M, N, device=cuda_dev, generator=gen) / N ** 0.5).bfloat16()
+    A = (torch.randn(r, K, device=cuda_dev, generator=gen) / K ** 0.5).bfloat16()
+    B = (torch.randn(N, r, device=cuda_dev, generator=gen) * 0.02).bfloat16()
+    outs = {}
+    for on in (False, True):
+        if on and (M * K) % 32 != 0:
+            continue
+        F._MASK_BITS = on
+        try:
+            u, us = F.lora_down(x, A, 0.25, seed, p)
+            du = F.lora_bwd_du(dy, B, 0.25)
+            dA, dB = torch.zeros_like(A), torch.zeros_like(B)
+            F.lora_grads(dy, x, u, du, 0.25, dA, dB, seed=seed, p=p)
+            torch.cuda.synchronize()
+            outs[on] = (u, us, dA, dB)
+        finally:
+            F._MASK_BITS = False
+    if True in outs:
+        for a, b in zip(outs[False], outs[True]):
+            assert torch.equal(a, b)

@@ -9,6 +9,7 @@ step "gpu tests (default configuration)" 600 python -m pytest tests -m gpu -x -q
 step "smoke" 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -1 gpurun_out/r2_smoke.log
 # experiments: parity first, timing only if parity holds
 B2Q_EXPERIMENTAL=1 step "variant 6 parity" 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "variant6 or linear_fwd_bwd" > gpurun_out/r2_v6_parity.log 2>&1; tail -2 gpurun_out/r2_v6_parity.log
+B2Q_EXPERIMENTAL=1 step "packed-mask parity" 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k mask_bits > gpurun_out/r2_maskbits_parity.log 2>&1; tail -2 gpurun_out/r2_maskbits_parity.log
 B2Q_GEMV_CFG=3 step "tensor-core GEMV parity" 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k gemv > gpurun_out/r2_gemv3_parity.log 2>&1; tail -2 gpurun_out/r2_gemv3_parity.log
 B2Q_DX_MASK_FIRST=1 step "mask-first dX parity" 300 python -m pytest tests -m gpu -x -q -k "dropout or hf or mlp" > gpurun_out/r2_maskfirst_parity.log 2>&1; tail -2 gpurun_out/r2_maskfirst_parity.log
 B2Q_EXPERIMENTAL=1 step "plain-C host example" 200 python -m pytest tests/test_gpu_c_host.py -m gpu -x -q > gpurun_out/r2_c_host.log 2>&1; tail -2 gpurun_out/r2_c_host.log
@@ -19,6 +20,7 @@ for v in 5 6; do step "phase trace fwd variant $v" 200 python tests/gpu_trace.py
 step "bench (default)" 600 python bench.py --no-cpu > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 B2Q_FWD_VARIANT=6 B2Q_DX_VARIANT=6 step "bench (variant 6)" 600 python bench.py --no-cpu --no-opt > gpurun_out/r2_bench_v6.json 2> gpurun_out/r2_bench_v6.err
 B2Q_DX_MASK_FIRST=1 step "bench (mask-first dX)" 600 python bench.py --no-cpu --no-opt > gpurun_out/r2_bench_maskfirst.json 2> gpurun_out/r2_bench_maskfirst.err
+B2Q_MASK_BITS=1 step "bench (packed mask)" 600 python bench.py --no-cpu --no-opt > gpurun_out/r2_bench_maskbits.json 2> gpurun_out/r2_bench_maskbits.err
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r2_bench_*.json")):
