@@ -158,8 +158,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-opt", action="store_true", help="skip the (reported-only) fused optimizer timing")
-    ap.add_argument("--e2e-timeout", type=float, default=90.0, help="N > 1 only: seconds after which the e2e phase is abandoned")
-    ap.add_argument("--global-timeout", type=float, default=420.0, help="N > 1 only: hard limit for the whole run")
+    ap.add_argument("--e2e-timeout", type=float, default=120.0, help="seconds after which the e2e phase is abandoned")
+    ap.add_argument("--global-timeout", type=float, default=420.0, help="hard limit for the whole run (any N)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -197,22 +197,41 @@ def main():
         except Exception:  # noqa: BLE001 -- diagnostics must not raise
             n = -1
         print(f"[bench rank {rank}] state dump ({why}): b2q launches so far {n}", file=sys.stderr, flush=True)
+        print_stalls()
         faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
         sys.stderr.flush()
 
-    if world > 1:
-        # global safety net at N > 1: never hold a multi-GPU box for minutes if a rank gets stuck before `value` exists
-        def global_timeout():
-            print(f"[bench rank {rank}] no result after {args.global_timeout:.0f} s -- giving up", file=sys.stderr, flush=True)
-            dump_state("global timeout")
-            os._exit(4)
-        g = threading.Timer(args.global_timeout, global_timeout)
-        g.daemon = True
-        g.start()
-        # last resort if the main thread is stuck while holding the GIL (the timers above then never run): faulthandler's
-        # watchdog is a C thread -- it dumps every Python stack and _exit(1)s without needing the interpreter
-        import faulthandler
-        faulthandler.dump_traceback_later(args.global_timeout + 30.0, exit=True, file=sys.stderr)
+    def stall_text():
+        """Records of the kernels' stall guard (include/b2q.h): host memory, readable after the context is lost."""
+        try:
+            return sys.modules["b200qlora"]._lib.stall_report() if "b200qlora" in sys.modules else ""
+        except Exception:  # noqa: BLE001 -- diagnostics must not raise
+            return ""
+
+    def print_stalls():
+        t = stall_text()
+        if t:
+            print(f"[bench rank {rank}] {t}", file=sys.stderr, flush=True)
+
+    # global safety net at every N: never hold a box for minutes if a rank gets stuck before `value` exists
+    def global_timeout():
+        print(f"[bench rank {rank}] no result after {args.global_timeout:.0f} s -- giving up", file=sys.stderr, flush=True)
+        dump_state("global timeout")
+        os._exit(4)
+    g = threading.Timer(args.global_timeout, global_timeout)
+    g.daemon = True
+    g.start()
+    # last resort if the main thread is stuck while holding the GIL (the timers above then never run): faulthandler's
+    # watchdog is a C thread -- it dumps every Python stack and _exit(1)s without needing the interpreter
+    import faulthandler
+    faulthandler.dump_traceback_later(args.global_timeout + 30.0, exit=True, file=sys.stderr)
+
+    def die(where, exc):
+        """A CUDA error (e.g. the stall guard's trap) in a device phase: report and leave without touching CUDA again."""
+        print(f"[bench rank {rank}] {where} failed: {type(exc).__name__}: {str(exc)[:600]}", file=sys.stderr, flush=True)
+        print_stalls()
+        sys.stderr.flush()
+        os._exit(3)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
@@ -269,29 +288,32 @@ def main():
     F.qlora_bwd_dx = timed(orig_dx, dx_flops)
 
     # ---- value: device-resident inputs, C-ABI ops back to back -------------------------------
-    for _ in range(args.warmup):
-        stack.step_direct(recompute=args.recompute)
-    barrier()
-    mark("value warm-up done")
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = F.launch_count()
-    timing_on[0] = True
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        stack.step_direct(recompute=args.recompute)
-    t1.record()
-    barrier()
-    timing_on[0] = False
-    launches = F.launch_count() - launches0
-    clocks = sampler.stop()
-    mark("value timed steps done")
-    ms = t0.elapsed_time(t1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    try:
+        for _ in range(args.warmup):
+            stack.step_direct(recompute=args.recompute)
+        barrier()
+        mark("value warm-up done")
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = F.launch_count()
+        timing_on[0] = True
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            stack.step_direct(recompute=args.recompute)
+        t1.record()
+        barrier()
+        timing_on[0] = False
+        launches = F.launch_count() - launches0
+        clocks = sampler.stop()
+        mark("value timed steps done")
+        ms = t0.elapsed_time(t1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+    except Exception as exc:  # noqa: BLE001 -- a CUDA error here (stall guard trap, launch failure) ends the run with a report
+        die("value phase", exc)
     value = M * world / (ms / 1e3)
 
     kern_ms = sum(a.elapsed_time(b) for a, b in main_events)
@@ -326,11 +348,8 @@ def main():
         return json.dumps(out)
 
     # ---- e2e: host buffers in, result out, inside the timed region ---------------------------------
-    # N = 1: through the module surface (LoraLinear4bit.forward + autograd).  N > 1: the same host-buffer step is first
-    # timed through the C-ABI operator calls (functional.* -- the path `value` uses, known to run clean on 4 and 8 GPUs),
-    # then through the module surface under a watchdog: the first module-surface step hung on a 4-GPU box in round 1
-    # (open issue), and if that happens again every rank reports the C-ABI end-to-end number and exits
-    # instead of holding the box until the NCCL watchdog fires.
+    # At every N: the step through the module surface (LoraLinear4bit.forward + autograd), activations copied from pinned
+    # host memory at the start of the step, squared gradient norm read back at its end.
     e2e = None
     e2e_guard = None
     if not args.no_e2e:
@@ -347,7 +366,6 @@ def main():
             return t if width == t.shape[1] else torch.cat([t] * reps, dim=1)[:, :width].contiguous()
 
         trace = os.environ.get("B2Q_BENCH_TRACE") == "1"   # diagnostic: synchronise + mark after every phase
-        interleaved = world > 1 and os.environ.get("B2Q_E2E_ORDER") != "all_forward_then_backward"
 
         def tmark(what):
             if trace:
@@ -362,7 +380,8 @@ def main():
             gos = {n: widen(dy, n) for n in widths_out}
             tmark("widen done")
             if modules:
-                g2 = stack.step_modules(ins, gos, tmark if trace else None, interleaved=interleaved)
+                g2 = stack.step_modules(ins, gos, tmark if trace else None,
+                                        interleaved=os.environ.get("B2Q_E2E_ORDER") == "per_module")
             else:
                 stack.step_direct(recompute=args.recompute, inputs=ins, grads_out=gos)
                 g2 = stack.grad_sqnorm()
@@ -394,34 +413,33 @@ def main():
 
         mark("e2e host buffers pinned")
         API_MODULES = "LoraLinear4bit.forward + autograd (QLoRALinear) -> C ABI"
-        API_C = "C-ABI operator calls (b200qlora.functional: lora_down, qlora_fwd, lora_bwd_du, qlora_bwd_dx, lora_grads)"
         ORDER_ALL = "forward of all modules, then backward of all"
-        if world > 1:
-            partial = {"e2e": None}   # what the watchdog reports: nothing yet, then the C-ABI end-to-end number
+        ORDER_PER = "per-module forward+backward, last module first (same kernels and launch count, no 50 GB of live outputs)"
+        interleaved = os.environ.get("B2Q_E2E_ORDER") == "per_module"
 
-            def e2e_timeout():
-                got = partial["e2e"]
-                mark("e2e phase timed out -- reporting " + ("`value` only" if got is None else "the C-ABI end-to-end number"))
-                dump_state("e2e timeout")
-                if rank == 0:
-                    what = ("the host-buffer step did not finish" if got is None else
-                            "e2e is the host-buffer step through the C-ABI operator calls; the module-surface step did not finish")
-                    print(result_line(got, None, None, note=f"{what} within {args.e2e_timeout:.0f} s at n_gpus={world} "
-                                      "(open issue, DESIGN.md); value / roofline are device-timed and complete"), flush=True)
-                sys.stdout.flush()
-                os._exit(0)
-            e2e_guard = threading.Timer(args.e2e_timeout, e2e_timeout)
-            e2e_guard.daemon = True
-            e2e_guard.start()
-            partial["e2e"] = time_e2e(False, API_C, ORDER_ALL)
-            # hedge: run autograd on the calling thread at N > 1 (the hang appeared when backward first ran on engine
-            # threads); B2Q_E2E_AUTOGRAD_THREADS=1 keeps the engine threads (tools/gpu_multi_diag.sh)
-            if os.environ.get("B2Q_E2E_AUTOGRAD_THREADS") != "1":
-                torch.autograd.set_multithreading_enabled(False)
-            e2e = time_e2e(True, API_MODULES, "per-module forward+backward (n_gpus > 1)" if interleaved else ORDER_ALL)
-            e2e["c_abi"] = {"value": partial["e2e"]["value"], "ms_per_step": partial["e2e"]["ms_per_step"]}
-        else:
-            e2e = time_e2e(True, API_MODULES, ORDER_ALL)
+        # The e2e phase runs under a watchdog at every N.  If it does not finish (or dies with a CUDA error -- the kernels'
+        # stall guard traps after ~3 s and leaves a report), rank 0 still prints the complete device-timed line with
+        # "e2e": null and a note, and the process exits non-zero within --e2e-timeout: never a box held for 30 minutes.
+        def e2e_failed(why):
+            mark("e2e phase failed: " + why)
+            dump_state("e2e failure")
+            if rank == 0:
+                note = (f"e2e phase did not complete at n_gpus={world}: {why}; value / roofline are device-timed and complete. "
+                        + stall_text()[:1500])
+                print(result_line(None, None, None, note=note), flush=True)
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(5)
+
+        e2e_guard = threading.Timer(args.e2e_timeout, lambda: e2e_failed(f"no result within {args.e2e_timeout:.0f} s"))
+        e2e_guard.daemon = True
+        e2e_guard.start()
+        try:
+            e2e = time_e2e(True, API_MODULES, ORDER_PER if interleaved else ORDER_ALL)
+        except Exception as exc:  # noqa: BLE001
+            e2e_failed(f"{type(exc).__name__}: {str(exc)[:300]}")
+        e2e_guard.cancel()
+        e2e_guard = None
 
     # ---- the step either side of the path: fused clip + AdamW on the flat buckets (reported, not part of `value`) ---
     opt_info = None
@@ -457,9 +475,9 @@ def main():
                              "fwd+bwd incl. NF4 decode in both passes (oracle/qlora.py); full-stack tokens/s "
                              "extrapolated linearly in FLOPs"}
         print(result_line(e2e, cpu, opt_info), flush=True)
+    faulthandler.cancel_dump_traceback_later()
+    g.cancel()
     if world > 1:
-        import faulthandler
-        faulthandler.cancel_dump_traceback_later()
         dist.destroy_process_group()
 
 

@@ -77,6 +77,10 @@ SIGNATURES = {
     "b2q_debug_set_trace": (c_int, [c_void_p, c_int]),
     "b2q_debug_set_prefetch": (c_int, [c_int]),
     "b2q_debug_set_mask_bits": (c_int, [c_void_p, c_i64]),
+    "b2q_debug_stall_count": (c_int, []),
+    "b2q_debug_stall_report": (c_int, [ct.c_char_p, c_size_t]),
+    "b2q_debug_stall_selftest": (c_int, [c_void_p]),
+    "b2q_debug_mbar_probe": (c_int, [c_void_p, c_void_p]),
     "b2q_launch_count": (c_u64, []),
 }
 
@@ -102,9 +106,21 @@ def load() -> ct.CDLL:
     return lib
 
 
+def stall_report() -> str:
+    """Text of the kernels' stall-guard records ('' when there are none).  Works after the CUDA context has been lost:
+    the records live in host memory (include/b2q.h, "Stall guard")."""
+    lib = load()
+    if lib.b2q_debug_stall_count() == 0:
+        return ""
+    buf = ct.create_string_buffer(1 << 16)
+    lib.b2q_debug_stall_report(buf, len(buf))
+    return buf.value.decode(errors="replace")
+
+
 def check(code: int, what: str) -> None:
     if code != 0:
         msg = load().b2q_error_string(code)
         detail = load().b2q_last_error_detail() if code < 0 else b""
+        stalls = stall_report() if code > 0 else ""
         raise RuntimeError(f"{what} failed: {msg.decode() if msg else code} (code {code})"
-                           + (f" [{detail.decode()}]" if detail else ""))
+                           + (f" [{detail.decode()}]" if detail else "") + (f"\n{stalls}" if stalls else ""))

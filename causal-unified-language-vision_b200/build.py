@@ -1,6 +1,9 @@
 """Builds libb2q.so (all CUDA kernels + the C ABI) for sm_100a with nvcc, in-tree.
 
-    python causal-unified-language-vision_b200/build.py [--force] [--verbose]
+    python causal-unified-language-vision_b200/build.py [--force] [--verbose] [--variant NAME -DMACRO=V ...]
+
+``--variant NAME`` builds ``libb2q_NAME.so`` with the extra ``-D`` switches (same-box A/B runs of two builds through
+``B2Q_LIB_PATH``; never loaded by default).
 """
 from __future__ import annotations
 
@@ -26,17 +29,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    out_path = OUT if not variant else os.path.join(HERE, f"libb2q_{variant}.so")
+    if not variant and not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build" if not variant else f"build_{variant}")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -47,13 +51,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+    link = [nvcc, "-shared", "-o", out_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
-    return OUT
+    return out_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=_variant,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -58,22 +58,36 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// Scopes: every wait / arrive below uses the PTX defaults (.acquire/.release at .cta scope), also
-// for arrives that target the peer CTA's barrier.  Operand tiles are produced by one CTA into its
-// own shared memory and consumed through the async proxy (TMA / UMMA); cluster-scope acquire or
-// release would add an L1 invalidate (CCTL.IVALL) or a wide MEMBAR per stage and buys nothing.
+// Scopes.  Barriers that only threads (and async operations) of ONE CTA touch use the PTX defaults (.acquire / .release
+// at .cta scope): pk_bar, pk_empty_bar, xf_bar, and everything in the single-CTA kernels.  In the cta_group::2 kernels
+// the peer CTA's producer, decode and epilogue warps arrive on the LEADER's full / "accumulator drained" barriers; a
+// .release.cta in CTA 1 does not synchronise-with an .acquire.cta in CTA 0 under the PTX memory model, so those arrives
+// use the `_xcta` forms below (.release.cluster) and the leader's waits on those barriers use mbar_try_wait_xcta
+// (.acquire.cluster).  B2Q_XCTA_SCOPE_CTA=1 (build switch) restores the round-1 .cta-scope forms for A/B timing.
+#ifndef B2Q_XCTA_SCOPE_CTA
+#define B2Q_XCTA_SCOPE_CTA 0
+#endif
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// `bar` is a shared::cluster address (own CTA's shared::cta addresses are valid ones)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+// `bar` is a shared::cluster address (own CTA's shared::cta addresses are valid ones); may name the peer's barrier
+__device__ __forceinline__ void mbar_arrive_xcta(uint32_t bar) {
+#if B2Q_XCTA_SCOPE_CTA
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+#else
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+__device__ __forceinline__ void mbar_arrive_expect_tx_xcta(uint32_t bar, uint32_t bytes) {
+#if B2Q_XCTA_SCOPE_CTA
     asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#else
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -88,9 +102,111 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
+// wait on a barrier of this CTA that threads of the peer CTA arrive on
+__device__ __forceinline__ uint32_t mbar_try_wait_xcta(uint32_t bar, uint32_t parity) {
+#if B2Q_XCTA_SCOPE_CTA
+    return mbar_try_wait(bar, parity);
+#else
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+#endif
+}
+
+// ------------------------------------------------------------ stall guard ----
+// Every pipeline wait is bounded.  A wait that has not been satisfied after STALL_LIMIT_CYCLES (about 2-3 s at
+// 1.3-2.0 GHz; the longest legitimate wait in these kernels is one output tile, < 0.1 ms) writes a record -- kernel
+// configuration, CTA, thread, wait site, barrier index and parity, tile / k-block, launch geometry and the raw 64-bit
+// state of every barrier of the CTA -- to a host-mapped buffer (StallSink::buf, owned by the host side of the library,
+// readable after the context is dead) and, a quarter of the limit later (so that the other stuck roles of the CTA get
+// their records out too), traps.  A lost arrive or a wrong parity therefore ends the process with a report
+// (b2q_debug_stall_report) instead of spinning until an external watchdog kills the job.
+#ifndef B2Q_STALL_GUARD
+#define B2Q_STALL_GUARD 1
+#endif
+constexpr long long STALL_LIMIT_CYCLES = 4000000000ll;
+constexpr uint32_t STALL_MAGIC = 0xB2517A11u;
+constexpr int STALL_MAX_RECORDS = 96;
+constexpr int STALL_MAX_BARS = 48;
+constexpr int STALL_HDR_WORDS = 16;                              // [0] record counter, [1] magic, rest reserved
+constexpr int STALL_REC_WORDS = 24 + 2 * STALL_MAX_BARS;         // header of the record + barrier words
+constexpr size_t STALL_BUF_BYTES = 4ull * (STALL_HDR_WORDS + STALL_MAX_RECORDS * STALL_REC_WORDS);
+
+struct StallSink {
+    uint32_t* buf;       // host-mapped record buffer (nullptr: trap without a record)
+    uint32_t bar_base;   // shared::cta address of barrier 0 of this CTA
+    uint32_t nbars;
+    uint32_t cfg;        // GemmCfg::ID
+    uint32_t geom[6];    // launch geometry: M, N, kb_main, kb_tail, splits, tiles
+    long long t0[32];    // per warp: clock64 at the first check of the wait in progress (scratch of stall_check)
+};
+
+__device__ __noinline__ void stall_record(const StallSink* sk, uint32_t bar, uint32_t parity, uint32_t site, int a,
+                                          int b) {
+    uint32_t* buf = sk->buf;
+    if (buf == nullptr) return;
+    const unsigned act = __activemask();
+    if ((threadIdx.x & 31u) != static_cast<unsigned>(__ffs(act) - 1)) return;   // one record per warp
+    const uint32_t slot = atomicAdd_system(buf, 1u);
+    if (slot >= static_cast<uint32_t>(STALL_MAX_RECORDS)) return;
+    volatile uint32_t* r = buf + STALL_HDR_WORDS + slot * STALL_REC_WORDS;
+    uint32_t smid, crank;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    r[1] = sk->cfg; r[2] = blockIdx.x; r[3] = threadIdx.x; r[4] = site; r[5] = (bar - sk->bar_base) >> 3;
+    r[6] = parity; r[7] = static_cast<uint32_t>(a); r[8] = static_cast<uint32_t>(b); r[9] = crank; r[10] = sk->nbars;
+    r[11] = smid; r[12] = act; r[13] = gridDim.x;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r[14 + i] = sk->geom[i];
+    const uint32_t nb = sk->nbars < static_cast<uint32_t>(STALL_MAX_BARS) ? sk->nbars : static_cast<uint32_t>(STALL_MAX_BARS);
+    for (uint32_t i = 0; i < nb; ++i) {
+        uint32_t lo, hi;
+        asm volatile("ld.volatile.shared::cta.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(sk->bar_base + 8u * i));
+        r[24 + 2 * i] = lo;
+        r[25 + 2 * i] = hi;
     }
+    __threadfence_system();
+    r[0] = STALL_MAGIC;   // record complete
+    __threadfence_system();
+}
+
+// Cold part of a bounded wait: called every 4096 failed probes with the probe count `n` (bit 31: record written).
+// The start time lives in the sink (one slot per warp: the lanes of a warp wait together), so the hot loop keeps a single
+// counter register.  Returns the new n.
+__device__ __noinline__ uint32_t stall_check(StallSink* sk, uint32_t n, uint32_t bar, uint32_t parity, uint32_t site,
+                                             int a, int b) {
+    const long long now = clock64();
+    volatile long long* t0 = &sk->t0[threadIdx.x >> 5];
+    if ((n & 0x7FFFFFFFu) == 0x1000u) { *t0 = now; return n; }
+    const long long dt = now - *t0;
+    if (dt > STALL_LIMIT_CYCLES && (n >> 31) == 0u) {
+        stall_record(sk, bar, parity, site, a, b);
+        n |= 0x80000000u;
+    }
+    if (dt > STALL_LIMIT_CYCLES + STALL_LIMIT_CYCLES / 4) __trap();
+    return n;
+}
+
+template <bool XCTA = false>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const StallSink* sk, uint32_t site, int a = 0,
+                                          int b = 0) {
+#if B2Q_STALL_GUARD
+    uint32_t n = 0;
+    while (!(XCTA ? mbar_try_wait_xcta(bar, parity) : mbar_try_wait(bar, parity))) {
+        if (((++n) & 0xFFFu) == 0u) n = stall_check(const_cast<StallSink*>(sk), n, bar, parity, site, a, b);
+    }
+#else
+    while (!(XCTA ? mbar_try_wait_xcta(bar, parity) : mbar_try_wait(bar, parity))) {
+    }
+#endif
 }
 
 // -------------------------------------------------------------------- TMA ----

@@ -3,14 +3,36 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <string>
 
 #include "qlora_gemm.cuh"
 
 namespace b2q {
 
 std::atomic<uint64_t> g_launch_count{0};
-static char g_last_error[512] = "";
+// Detail text of the last B2Q_ERR_* raised on the calling thread (autograd engine threads call in concurrently).
+static thread_local char g_last_error[512] = "";
 void set_error_detail(const char* msg) { snprintf(g_last_error, sizeof(g_last_error), "%s", msg); }
+
+// ---------------------------------------------------------------- stall guard ----
+// One host-mapped, portable record buffer per process: the kernels' bounded waits (b2q_ptx.cuh) write their records
+// here before they trap, and the host can still read it when the CUDA context is gone.
+static uint32_t* g_stall_host = nullptr;
+static std::once_flag g_stall_once;
+static uint32_t* stall_buffer() {
+    std::call_once(g_stall_once, [] {
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, STALL_BUF_BYTES, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess && h != nullptr) {
+            memset(h, 0, STALL_BUF_BYTES);
+            static_cast<uint32_t*>(h)[1] = STALL_MAGIC;
+            g_stall_host = static_cast<uint32_t*>(h);   // unified addressing: the host pointer is the device pointer
+        } else {
+            (void)cudaGetLastError();   // no buffer: the kernels still trap, without a record
+        }
+    });
+    return g_stall_host;
+}
 
 // ---------------------------------------------------------------- tensor maps ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -19,15 +41,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static EncodeTiledFn get_encode_fn() {
     static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;   // autograd engine threads may race the main thread here
+    std::call_once(once, [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
             fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
+    });
     return fn;
 }
 
@@ -182,6 +203,7 @@ static int launch(GemmParams& p, cudaStream_t stream) {
         attr_set.fetch_or(bit, std::memory_order_relaxed);
     }
     if (g_pdl < 0) { const char* v = getenv("B2Q_PDL"); g_pdl = v ? atoi(v) : 0; }   // opt-in: no measurable gain
+    p.stall_buf = stall_buffer();
     p.trace = g_trace;
     p.trace_tiles = g_trace_tiles;
     p.pf_dist = g_pf_dist;
@@ -290,6 +312,116 @@ extern "C" const char* b2q_error_string(int code) {
         case B2Q_ERR_COMM: return "b2q: NCCL unavailable or an NCCL call failed";
         default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "b2q: unknown error";
     }
+}
+
+// ---- stall report ------------------------------------------------------------------------------------------------
+static const char* stall_site_name(uint32_t site) {
+    switch (site) {
+        case 1: return "operand producer: stage free (empty_bar)";
+        case 2: return "operand producer: drain (empty_bar)";
+        case 3: return "UMMA issuer: operands ready (full_bar / xf_bar)";
+        case 4: return "UMMA issuer: accumulator drained (tempty_bar)";
+        case 5: return "packed producer: slot free (pk_empty_bar)";
+        case 6: return "epilogue: accumulator complete (tfull_bar)";
+        case 7: return "epilogue: sub-tile 1 complete (tfull1_bar)";
+        case 8: return "A transform: operand landed (full_bar)";
+        case 9: return "decode: packed bytes landed (pk_bar)";
+        case 10: return "decode: B stage free (empty_bar)";
+        case 11: return "decode, LoRA tail k-block: stage free (empty_bar)";
+        case 12: case 14: return "UMMA issuer (run-ahead): accumulator drained (tempty_bar)";
+        case 13: case 15: return "UMMA issuer (run-ahead): operands ready (full_bar)";
+        default: return "?";
+    }
+}
+
+extern "C" int b2q_debug_stall_count(void) {
+    return g_stall_host != nullptr ? static_cast<int>(*reinterpret_cast<volatile uint32_t*>(g_stall_host)) : 0;
+}
+
+extern "C" int b2q_debug_stall_report(char* out, size_t cap) {
+    if (out != nullptr && cap > 0) out[0] = 0;
+    if (g_stall_host == nullptr) return 0;
+    const volatile uint32_t* h = g_stall_host;
+    const int n = static_cast<int>(h[0]);
+    if (out == nullptr || cap == 0) return n;
+    std::string t;
+    char line[512];
+    const int shown = n < STALL_MAX_RECORDS ? n : STALL_MAX_RECORDS;
+    snprintf(line, sizeof(line), "b2q stall guard: %d record(s)\n", n);
+    t += line;
+    for (int i = 0; i < shown; ++i) {
+        const volatile uint32_t* r = h + STALL_HDR_WORDS + i * STALL_REC_WORDS;
+        if (r[0] != STALL_MAGIC) { snprintf(line, sizeof(line), "  [%d] (incomplete)\n", i); t += line; continue; }
+        const uint32_t c = r[1];
+        snprintf(line, sizeof(line),
+                 "  [%d] cfg 0x%x {CG %u MT %u BN %u A_MN %u B_MN %u B_DEC %u EPI %u STAGES %u A_XF %u STG %s ESETS %u RA %u} "
+                 "cta %u/%u (cluster rank %u, sm %u) thread %u (warp %u) site %u <%s> barrier #%u parity %u tile %d kb %d | "
+                 "M %u N %u kb_main %u kb_tail %u splits %u tiles %u\n",
+                 i, c, c & 3u, (c >> 2) & 3u, ((c >> 4) & 15u) * 64u, (c >> 8) & 1u, (c >> 9) & 1u, (c >> 10) & 1u,
+                 (c >> 11) & 3u, (c >> 13) & 15u, (c >> 17) & 1u, ((c >> 18) & 1u) ? "coal" : ((c >> 19) & 1u) ? "tma" : "row",
+                 ((c >> 20) & 1u) + 1u, (c >> 21) & 7u, r[2], r[13], r[9], r[11], r[3], r[3] >> 5, r[4], stall_site_name(r[4]),
+                 r[5], r[6], static_cast<int>(r[7]), static_cast<int>(r[8]), r[14], r[15], r[16], r[17], r[18], r[19]);
+        t += line;
+        const uint32_t nb = r[10] < static_cast<uint32_t>(STALL_MAX_BARS) ? r[10] : static_cast<uint32_t>(STALL_MAX_BARS);
+        t += "      barrier words:";
+        for (uint32_t b = 0; b < nb; ++b) {
+            snprintf(line, sizeof(line), " %u:%08x_%08x", b, r[25 + 2 * b], r[24 + 2 * b]);
+            t += line;
+        }
+        t += "\n";
+    }
+    snprintf(out, cap, "%s", t.c_str());
+    return n;
+}
+
+// One CTA, one barrier that expects two arrivals and gets one: the wait must end in a record + trap.
+__global__ void stall_selftest_kernel(uint32_t* stall_buf) {
+    __shared__ alignas(8) uint64_t bar;
+    __shared__ StallSink sink;
+    const uint32_t b = smem_u32(&bar);
+    if (threadIdx.x == 0) {
+        mbar_init(b, 2);
+        fence_mbar_init();
+        sink.buf = stall_buf; sink.bar_base = b; sink.nbars = 1; sink.cfg = 0;
+        for (int i = 0; i < 6; ++i) sink.geom[i] = 0;
+        mbar_arrive(b);
+    }
+    __syncthreads();
+    mbar_wait(b, 0, &sink, 6, 123, 45);
+}
+
+extern "C" int b2q_debug_stall_selftest(cudaStream_t stream) {
+    stall_selftest_kernel<<<1, 64, 0, stream>>>(stall_buffer());
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+// Raw barrier words after a scripted sequence (key for reading stall records): out[0] init(count 5); [1] + 1 arrive;
+// [2] + 2 arrives; [3] + arrive.expect_tx(4096); [4] + last arrive (count met, 4096 tx bytes pending); [5] init(count 1)
+// then 1 arrive (phase 0 complete); [6] same barrier after a second arrive (phase 1 complete); [7] init(count 3).
+__global__ void mbar_probe_kernel(unsigned long long* out) {
+    __shared__ alignas(8) unsigned long long bars[3];
+    if (threadIdx.x != 0) return;
+    const uint32_t b0 = smem_u32(&bars[0]), b1 = smem_u32(&bars[1]), b2 = smem_u32(&bars[2]);
+    auto rd = [](uint32_t b) { unsigned long long v; asm volatile("ld.volatile.shared::cta.u64 %0, [%1];" : "=l"(v) : "r"(b)); return v; };
+    mbar_init(b0, 5); mbar_init(b1, 1); mbar_init(b2, 3);
+    fence_mbar_init();
+    out[0] = rd(b0);
+    mbar_arrive(b0); out[1] = rd(b0);
+    mbar_arrive(b0); out[2] = rd(b0);
+    mbar_arrive_expect_tx(b0, 4096); out[3] = rd(b0);
+    mbar_arrive(b0); mbar_arrive(b0); out[4] = rd(b0);
+    mbar_arrive(b1); out[5] = rd(b1);
+    mbar_arrive(b1); out[6] = rd(b1);
+    out[7] = rd(b2);
+    for (int i = 8; i < 16; ++i) out[i] = 0;
+}
+
+extern "C" int b2q_debug_mbar_probe(uint64_t* out_words, cudaStream_t stream) {
+    if (out_words == nullptr) return B2Q_ERR_ARG;
+    mbar_probe_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<unsigned long long*>(out_words));
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
 }
 
 extern "C" int b2q_debug_set_mask_bits(const void* bits, int64_t bytes) {

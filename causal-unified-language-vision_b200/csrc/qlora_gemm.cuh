@@ -75,6 +75,8 @@ struct GemmParams {
     // experiment (XF_BITS configs): packed LoRA-dropout mask of the activation, bit k of byte b = keep(8 b + k)
     const uint8_t* mask_bits;
     long long mask_bytes;   // size of mask_bits (rows of the operand tile past the activation read nothing)
+    // stall guard (b2q_ptx.cuh): host-mapped record buffer of the library, or nullptr
+    uint32_t* stall_buf;
 };
 
 template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_, int NG_ = 2,
@@ -83,6 +85,13 @@ struct GemmCfg {
     // XF_BITS (experiment): the A-operand transform reads the packed mask (GemmParams::mask_bits) instead of hashing.
     static constexpr bool XF_BITS = XF_BITS_;
     static_assert(!XF_BITS_ || A_XF_, "XF_BITS is a mode of the A-operand transform");
+    // configuration id carried by stall records (decoded by b2q_debug_stall_report)
+    static constexpr uint32_t ID = static_cast<uint32_t>(CG_) | (static_cast<uint32_t>(MT_) << 2) |
+                                   (static_cast<uint32_t>(BN_ / 64) << 4) | (A_MN_ ? 1u << 8 : 0u) | (B_MN_ ? 1u << 9 : 0u) |
+                                   (B_DEC_ ? 1u << 10 : 0u) | (static_cast<uint32_t>(EPI_) << 11) |
+                                   (static_cast<uint32_t>(STAGES_) << 13) | (A_XF_ ? 1u << 17 : 0u) |
+                                   (STG_ < 0 ? 1u << 18 : 0u) | (STG_ > 0 ? 1u << 19 : 0u) | (ESETS_ == 2 ? 1u << 20 : 0u) |
+                                   (static_cast<uint32_t>(RA_) << 21) | (XF_BITS_ ? 1u << 24 : 0u);
     // RA > 0 (experiment, MT == 2 with a single accumulator stage): the UMMA issuer reorders the first and the last RA
     // k-blocks of a tile.  Head: sub-tile 0 of the first RA k-blocks as soon as the epilogue has drained sub-tile 0 of the
     // previous tile, then sub-tile 1 of the same k-blocks (releasing their operand stages) once sub-tile 1 is drained
@@ -199,7 +208,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     constexpr int NB1 = NB0 + 2 * PST + (Cfg::A_XF ? STAGES : 0);
     [[maybe_unused]] auto tfull1_bar = [&](int a) { return bar_base + 8u * (NB1 + a); };
     constexpr int NBARS = NB1 + (Cfg::RA > 0 ? ACC_STAGES : 0);
-    static_assert(8 * NBARS + 8 <= Cfg::BAR_BYTES, "barrier area");
+    static_assert(8 * NBARS + 16 + sizeof(StallSink) <= Cfg::BAR_BYTES && NBARS <= STALL_MAX_BARS, "barrier area");
+    const StallSink* sk = reinterpret_cast<const StallSink*>(smem_gen + Cfg::RING_BYTES + 8 * NBARS + 16);
     const uint32_t tmem_slot = bar_base + 8u * NBARS;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::RING_BYTES + 8 * NBARS);
     float* code256_s = reinterpret_cast<float*>(smem_gen + Cfg::RING_BYTES + Cfg::BAR_BYTES);
@@ -243,6 +253,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             for (int mt = 0; mt < MT; ++mt) mbar_init(tempty_bar(a, mt), CG * 4);  // one arrive per epilogue warp, both CTAs
         }
         fence_mbar_init();
+        StallSink* skw = const_cast<StallSink*>(sk);
+        skw->buf = p.stall_buf; skw->bar_base = bar_base; skw->nbars = NBARS; skw->cfg = Cfg::ID;
+        skw->geom[0] = static_cast<uint32_t>(p.M); skw->geom[1] = static_cast<uint32_t>(p.N);
+        skw->geom[2] = static_cast<uint32_t>(p.kb_main); skw->geom[3] = static_cast<uint32_t>(p.kb_tail);
+        skw->geom[4] = static_cast<uint32_t>(p.splits); skw->geom[5] = static_cast<uint32_t>(num_tiles);
     }
     if (warp == Cfg::W_ALLOC) {
         tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
@@ -281,11 +296,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     const bool tail = kb >= p.kb_main;
                     const int k0 = tail ? (kb - p.kb_main) * 64 : (kb0 + kb) * 64;
                     const CUtensorMap* mapA = tail ? &p.tmA2 : &p.tmA;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_wait(empty_bar(s), ph ^ 1u, sk, 1, tile, kb);
                     const bool b_by_tma = tail || !Cfg::B_DEC;
                     const uint32_t tx = Cfg::A_BYTES + (b_by_tma ? Cfg::B_BYTES : 0);
                     const uint32_t fb = full_bar_arrive(s);
-                    if constexpr (CG == 2) mbar_arrive_expect_tx_cluster(fb, tx); else mbar_arrive_expect_tx(fb, tx);
+                    if constexpr (CG == 2) mbar_arrive_expect_tx_xcta(fb, tx); else mbar_arrive_expect_tx(fb, tx);
                     auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
                         if constexpr (CG == 2) tma_load_2d_pair(dst, map, fb, c0, c1); else tma_load_2d(dst, map, fb, c0, c1);
                     };
@@ -324,7 +339,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             }
             // drain: every tcgen05.commit aimed at this CTA's empty barriers has landed before exit
             for (int i = 0; i < STAGES; ++i) {
-                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_wait(empty_bar(s), ph ^ 1u, sk, 2, -1, i);
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                             w0 = clock64();
                             if (kb == 0) tr[0] = w0;
                         }
-                        mbar_wait(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph);
+                        mbar_wait<CG == 2>(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph, sk, 3, tile, kb);
                         tc_fence_after();
                         if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
                         const uint64_t a_base = Cfg::A_MN ? umma_desc_sw128(a_stage(s), 8192, 1024) : umma_desc_sw128(a_stage(s), 16, 1024);
@@ -357,7 +372,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         for (int mt = 0; mt < MT; ++mt) {
                             if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
                                 if (tr != nullptr && mt == 0) tr[1] = clock64();
-                                mbar_wait(tempty_bar(as, mt), aph ^ 1u);
+                                mbar_wait<CG == 2>(tempty_bar(as, mt), aph ^ 1u, sk, 4, tile, mt);
                                 tc_fence_after();
                                 if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
                             }
@@ -399,19 +414,19 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         const int ra = kb_total < Cfg::RA ? kb_total : Cfg::RA;
                         const int rt = (kb_total - ra) < Cfg::RA ? (kb_total - ra) : Cfg::RA;   // tail window, see below
                         if (tr != nullptr) tr[0] = tr[1] = clock64();
-                        mbar_wait(tempty_bar(as, 0), aph ^ 1u);
+                        mbar_wait<CG == 2>(tempty_bar(as, 0), aph ^ 1u, sk, 12, tile, 0);
                         tc_fence_after();
                         if (tr != nullptr) tr[2] = clock64();
                         int s2 = s;
                         for (int kb = 0; kb < ra; ++kb) {
                             // (ra < STAGES: the window wraps the ring at most once; a wrapped stage is one phase further)
-                            mbar_wait(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph);
+                            mbar_wait<CG == 2>(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph, sk, 13, tile, kb);
                             tc_fence_after();
                             issue_mt(s2, 0, kb);
                             if (kb == kb_total - 1) umma_commit<CG>(tfull_bar(as));
                             if (++s2 == STAGES) s2 = 0;
                         }
-                        mbar_wait(tempty_bar(as, 1), aph ^ 1u);
+                        mbar_wait<CG == 2>(tempty_bar(as, 1), aph ^ 1u, sk, 14, tile, 1);
                         tc_fence_after();
                         if (tr != nullptr) tr[3] = clock64();
                         for (int kb = 0; kb < ra; ++kb) {
@@ -432,14 +447,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                             w0 = clock64();
                             if (kb == 0) tr[0] = w0;
                         }
-                        mbar_wait(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph);
+                        mbar_wait<CG == 2>(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph, sk, 3, tile, kb);
                         tc_fence_after();
                         if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
     #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
                                 if (tr != nullptr && mt == 0) tr[1] = clock64();
-                                mbar_wait(tempty_bar(as, mt), aph ^ 1u);
+                                mbar_wait<CG == 2>(tempty_bar(as, mt), aph ^ 1u, sk, 4, tile, mt);
                                 tc_fence_after();
                                 if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
                             }
@@ -462,7 +477,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         if (rt > 0) {
                             int s2 = s;
                             for (int kb = kb_end; kb < kb_total; ++kb) {
-                                mbar_wait(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph);
+                                mbar_wait<CG == 2>(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph, sk, 15, tile, kb);
                                 tc_fence_after();
                                 issue_mt(s2, 0, kb);
                                 if (++s2 == STAGES) s2 = 0;
@@ -493,7 +508,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 const int kb0 = split * p.kb_main;
                 for (int kb = 0; kb < p.kb_main; ++kb) {
                     const int k0 = (kb0 + kb) * 64;
-                    mbar_wait(pk_empty_bar(ps), pph ^ 1u);
+                    mbar_wait(pk_empty_bar(ps), pph ^ 1u, sk, 5, tile, kb);
                     mbar_arrive_expect_tx(pk_bar(ps), Cfg::P_BYTES);
                     if constexpr (!Cfg::B_MN)
                         tma_load_2d(p_stage(ps), &p.tmB, pk_bar(ps), k0 / 2, brow0);   // box 32 B x BNC rows of W
@@ -518,7 +533,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             const int n0 = nt_i * BN;
             long long* tr = (p.trace != nullptr && tseq < p.trace_tiles && wq == 0 && lane == 0)
                                 ? p.trace + (static_cast<long long>(blockIdx.x) * p.trace_tiles + tseq) * 8 : nullptr;
-            mbar_wait(tfull_bar(as), aph);
+            mbar_wait(tfull_bar(as), aph, sk, 6, tile, 0);
             tc_fence_after();
             if (tr != nullptr) tr[5] = clock64();
             if constexpr (Cfg::EPI_COAL || Cfg::EPI_TMA) {
@@ -539,7 +554,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     const int mt = q / GPM, c = q % GPM;
                     if constexpr (Cfg::RA > 0) {
                         if (q == GPM) {   // first group of sub-tile 1: its MMAs are committed separately
-                            mbar_wait(tfull1_bar(as), aph);
+                            mbar_wait(tfull1_bar(as), aph, sk, 7, tile, q);
                             tc_fence_after();
                         }
                     }
@@ -582,7 +597,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
-                            if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar_arrive(as, mt)); else mbar_arrive(tempty_bar(as, mt));
+                            if constexpr (CG == 2) mbar_arrive_xcta(tempty_bar_arrive(as, mt)); else mbar_arrive(tempty_bar(as, mt));
                         }
                     }
                     if constexpr (Cfg::EPI_TMA) {
@@ -714,7 +729,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 tc_fence_before();   // sub-tile mt drained
                 __syncwarp();
                 if (lane == 0) {
-                    if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar_arrive(as, mt)); else mbar_arrive(tempty_bar(as, mt));
+                    if constexpr (CG == 2) mbar_arrive_xcta(tempty_bar_arrive(as, mt)); else mbar_arrive(tempty_bar(as, mt));
                 }
             }
             if (tr != nullptr) tr[6] = clock64();
@@ -746,7 +761,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             for (int kb = static_cast<int>((static_cast<uint32_t>(g) - it) & (XG - 1)); kb < kb_total; kb += XG) {
                 const int k0 = (kb0 + kb) * 64;
                 const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
-                if constexpr (!Cfg::XF_BITS) mbar_wait(full_bar(s), ph);
+                if constexpr (!Cfg::XF_BITS) mbar_wait(full_bar(s), ph, sk, 8, tile, kb);
                 // hash counter of chunk i = counter of chunk 0 + a multiple of xf_ld (XT = 128: rows advance by 16 per chunk)
                 uint32_t j0_base;
                 {
@@ -767,7 +782,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         const uint32_t bi = j0 >> 1;
                         mb[i] = bi < mask_bytes32 ? static_cast<uint32_t>(__ldg(p.mask_bits + bi)) : 0xFFu;   // past the activation: zeros anyway
                     }
-                    mbar_wait(full_bar(s), ph);
+                    mbar_wait(full_bar(s), ph, sk, 8, tile, kb);
 #pragma unroll
                     for (int i = 0; i < 1024 / XT; ++i) {
                         const uint32_t addr = a_stage(s) + (t + XT * i) * 16;
@@ -853,7 +868,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 Nf4Lut lut;
                 nf4_build_lut(code16, a, lut);
                 const uint32_t pi = pit + kb, ps = pi % PST, pph = (pi / PST) & 1u;
-                mbar_wait(pk_bar(ps), pph);
+                mbar_wait(pk_bar(ps), pph, sk, 9, tile, kb);
                 uint32_t w[8];
                 {
                     const uint32_t src = p_stage(ps) + t * 32;
@@ -865,7 +880,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pk_empty_bar(ps));  // packed slot may be refilled
                 const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);              // decoded-B slot free (MMAs that read it retired)
+                mbar_wait(empty_bar(s), ph ^ 1u, sk, 10, tile, kb);   // decoded-B slot free (MMAs that read it retired)
                 const uint32_t dst = b_stage(s) + dst_off;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -877,7 +892,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if constexpr (CG == 2) mbar_arrive_cluster(full_bar_arrive(s)); else mbar_arrive(full_bar(s));
+                    if constexpr (CG == 2) mbar_arrive_xcta(full_bar_arrive(s)); else mbar_arrive(full_bar(s));
                 }
             }
             // LoRA tail k-blocks: B arrives by TMA; the group that owns the ring position keeps the count
@@ -885,10 +900,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 const uint32_t si = it + kb;
                 if ((si & (NG - 1)) != static_cast<uint32_t>(g)) continue;
                 const uint32_t s = si % STAGES, ph = (si / STAGES) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_wait(empty_bar(s), ph ^ 1u, sk, 11, tile, kb);
                 __syncwarp();
                 if (lane == 0) {
-                    if constexpr (CG == 2) mbar_arrive_cluster(full_bar_arrive(s)); else mbar_arrive(full_bar(s));
+                    if constexpr (CG == 2) mbar_arrive_xcta(full_bar_arrive(s)); else mbar_arrive(full_bar(s));
                 }
             }
             it += kb_total;

@@ -227,6 +227,20 @@ int b2q_debug_set_mask_bits(const void* bits, int64_t bytes);
 /* Tuning: L2 prefetch distance (in 64-wide k-blocks) of the activation operand in the tcgen05 GEMMs; 0 = off. */
 int b2q_debug_set_prefetch(int kblocks);
 
+/* Stall guard.  Every pipeline wait inside the tcgen05 kernels is bounded (about 2-3 s): a wait that expires writes a
+ * record (kernel configuration, CTA, thread, wait site, barrier index / parity, tile, k-block, launch geometry and the raw
+ * state of every barrier of the CTA) to a host-mapped buffer owned by the library and then traps, so a lost arrive ends
+ * the process with a CUDA error and a report instead of a silent spin.  b2q_debug_stall_count: records written so far in
+ * this process (0 in a healthy run).  b2q_debug_stall_report: formats them into `out` (NUL-terminated, truncated to
+ * `cap`), returns the record count; usable after the CUDA context has been lost.  b2q_debug_stall_selftest launches a
+ * one-CTA kernel whose barrier never completes (the calling process loses its context a few seconds later: run it in
+ * a child process); b2q_debug_mbar_probe writes the raw 64-bit state of a barrier after a scripted sequence of
+ * operations to out_words[16] (device memory) -- the key for reading the barrier words of a record. */
+int b2q_debug_stall_count(void);
+int b2q_debug_stall_report(char* out, size_t cap);
+int b2q_debug_stall_selftest(cudaStream_t stream);
+int b2q_debug_mbar_probe(uint64_t* out_words, cudaStream_t stream);
+
 /* Launch counter (every kernel this library launches increments it); for bench.py's gpu_launches. */
 uint64_t b2q_launch_count(void);
 
