@@ -115,7 +115,10 @@ extern "C" int b2q_comm_init(b2q_comm** comm_out, const void* id, size_t id_byte
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess) {   // release whatever was created before the failing call
+        if (c->done != nullptr) cudaEventDestroy(c->done);
+        if (c->ready != nullptr) cudaEventDestroy(c->ready);
+        if (c->stream != nullptr) cudaStreamDestroy(c->stream);
         delete c;
         return static_cast<int>(e);
     }

@@ -328,6 +328,8 @@ static const char* stall_site_name(uint32_t site) {
         case 9: return "decode: packed bytes landed (pk_bar)";
         case 10: return "decode: B stage free (empty_bar)";
         case 11: return "decode, LoRA tail k-block: stage free (empty_bar)";
+        case 16: return "A transform: previous use of the stage released (empty_bar)";
+        case 17: return "decode: previous use of the packed slot released (pk_empty_bar)";
         case 12: case 14: return "UMMA issuer (run-ahead): accumulator drained (tempty_bar)";
         case 13: case 15: return "UMMA issuer (run-ahead): operands ready (full_bar)";
         default: return "?";
@@ -403,7 +405,11 @@ __global__ void mbar_probe_kernel(unsigned long long* out) {
     __shared__ alignas(8) unsigned long long bars[3];
     if (threadIdx.x != 0) return;
     const uint32_t b0 = smem_u32(&bars[0]), b1 = smem_u32(&bars[1]), b2 = smem_u32(&bars[2]);
-    auto rd = [](uint32_t b) { unsigned long long v; asm volatile("ld.volatile.shared::cta.u64 %0, [%1];" : "=l"(v) : "r"(b)); return v; };
+    auto rd = [](uint32_t b) {
+        uint32_t lo, hi;
+        asm volatile("ld.volatile.shared::cta.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(b) : "memory");
+        return (static_cast<unsigned long long>(hi) << 32) | lo;
+    };
     mbar_init(b0, 5); mbar_init(b1, 1); mbar_init(b2, 3);
     fence_mbar_init();
     out[0] = rd(b0);

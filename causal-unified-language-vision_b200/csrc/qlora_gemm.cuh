@@ -761,6 +761,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             for (int kb = static_cast<int>((static_cast<uint32_t>(g) - it) & (XG - 1)); kb < kb_total; kb += XG) {
                 const int k0 = (kb0 + kb) * 64;
                 const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
+                // Consecutive uses of a stage are transformed by DIFFERENT groups whenever XG does not divide STAGES, and
+                // a parity wait cannot tell "use u has landed" from "use u-1 has not landed yet".  A group that runs
+                // ahead (its previous stage landed before an older load did -- TMA completions are not ordered) would
+                // transform the stage one use early and complete xf_bar(s) twice before the issuer looked once: the
+                // round-1 stall.  Waiting first for the previous use of the stage to be RELEASED
+                // (empty_bar phase u-1: exact, because this group's previous position si-XG was issued by the producer
+                // after it had seen phase u-2) puts full_bar(s) at phase >= u, which makes the parity wait exact too.
+                static_assert(XG <= STAGES, "transform groups: the producer-order argument above needs XG <= STAGES");
+                mbar_wait(empty_bar(s), ph ^ 1u, sk, 16, tile, kb);
                 if constexpr (!Cfg::XF_BITS) mbar_wait(full_bar(s), ph, sk, 8, tile, kb);
                 // hash counter of chunk i = counter of chunk 0 + a multiple of xf_ld (XT = 128: rows advance by 16 per chunk)
                 uint32_t j0_base;
@@ -868,6 +877,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 Nf4Lut lut;
                 nf4_build_lut(code16, a, lut);
                 const uint32_t pi = pit + kb, ps = pi % PST, pph = (pi / PST) & 1u;
+                // The group that reads packed slot ps alternates at tile boundaries when kb_tail is odd (`it` and `pit`
+                // drift apart by one per tile), so this group may not have seen the slot's previous use: wait until that
+                // use has been released by its readers (pk_empty_bar phase u-1 -- exact: this group's previous position
+                // pi-1 or pi-2 was issued by the producer after it had seen phase u-2), after which pk_bar(ps) is at
+                // phase >= u and the parity wait below cannot alias "use u-1 not landed yet" with "use u landed".
+                static_assert(NG <= PST, "decode groups: the producer-order argument above needs NG <= PST");
+                mbar_wait(pk_empty_bar(ps), pph ^ 1u, sk, 17, tile, kb);
                 mbar_wait(pk_bar(ps), pph, sk, 9, tile, kb);
                 uint32_t w[8];
                 {

@@ -10,6 +10,12 @@ What it replaces in the reference, for the trainable LoRA parameters:
 exactly like ``GradSync``'s gradient buckets (``param.data`` becomes a view), keeps both moments flat, and runs ONE
 kernel per bucket (14 bytes of HBM traffic per element) after the gradient all-reduce has finished; the clip
 coefficient is computed on the device from per-block partial sums, so a step needs no host synchronisation.
+
+The reference's optimizer and clip cover ALL trainable parameters -- besides the LoRA weights that is
+``multi_modal_projector`` (/root/reference/cullavo/load_cullavo.py:128-130).  Parameters registered with
+``GradSync(extra_params=...)`` are therefore part of this optimizer too: their squared gradient norm enters the global
+norm, the same clip coefficient scales their gradients, and a stock ``torch.optim.AdamW`` with the same
+hyper-parameters (sharing ``param_groups[0]['lr']``, so one scheduler drives both) steps them.
 """
 from __future__ import annotations
 
@@ -50,6 +56,10 @@ class FusedLoraAdamW(torch.optim.Optimizer):
             self.mflat.append(torch.zeros(b.flat.numel(), dtype=state_dtype, device=b.flat.device))
             self.vflat.append(torch.zeros(b.flat.numel(), dtype=state_dtype, device=b.flat.device))
         self.state_dtype = state_dtype
+        self.extra_params = list(sync.extra_params)
+        self.extra_optimizer = (torch.optim.AdamW(self.extra_params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+                                if self.extra_params else None)
+        self._extra_coef: Optional[torch.Tensor] = None
         self._step = 0
         self._max_norm = 0.0
         self._partials: Optional[torch.Tensor] = None
@@ -59,10 +69,15 @@ class FusedLoraAdamW(torch.optim.Optimizer):
     def _compute_partials(self) -> torch.Tensor:
         lib = _lib.load()
         counts = [int(lib.b2q_sqnorm_blocks(b.flat.numel())) for b in self.sync.buckets]
-        total = sum(counts)
+        total = sum(counts) + 1   # last slot: squared gradient norm of the non-LoRA trainable parameters (0 if none)
         dev = self.sync.device
         if self._partials is None or self._partials.numel() != total:
             self._partials = torch.zeros(total, dtype=torch.float32, device=dev)
+        grads = [p.grad for p in self.extra_params if p.grad is not None]
+        if grads:
+            self._partials[total - 1] = torch.stack([g.float().pow(2).sum() for g in grads]).sum()
+        else:
+            self._partials[total - 1] = 0.0
         off = 0
         for b, c in zip(self.sync.buckets, counts):
             _need_cuda(b.flat)
@@ -78,7 +93,10 @@ class FusedLoraAdamW(torch.optim.Optimizer):
         host sync).  Same formula as ``torch.nn.utils.clip_grad_norm_``; the scaling itself is fused into the step."""
         self.sync.finish()  # the all-reduced gradients are what gets clipped
         self._max_norm = float(max_norm)
-        return self._compute_partials().sum().sqrt()
+        norm = self._compute_partials().sum().sqrt()
+        if self.extra_params:   # the fused kernel scales the LoRA gradients; the others are scaled here, same coefficient
+            self._extra_coef = torch.clamp(self._max_norm / (norm + 1e-6), max=1.0)
+        return norm
 
     # ---- torch.optim.Optimizer surface ---------------------------------------------------
     @torch.no_grad()
@@ -100,6 +118,14 @@ class FusedLoraAdamW(torch.optim.Optimizer):
                                           float(g["eps"]), float(g["weight_decay"]), self._step, _p(partials),
                                           0 if partials is None else partials.numel(), self._max_norm, _stream()),
                        "b2q_adamw_step")
+        if self.extra_optimizer is not None:
+            if self._max_norm > 0.0 and self._extra_coef is not None:
+                grads = [p.grad for p in self.extra_params if p.grad is not None]
+                if grads:
+                    torch._foreach_mul_(grads, self._extra_coef)
+            self.extra_optimizer.param_groups[0]["lr"] = g["lr"]
+            self.extra_optimizer.step()
+        self._extra_coef = None
         self._partials_valid = False
         self._max_norm = 0.0  # like the reference, clipping is requested per step
         return loss
@@ -107,15 +133,21 @@ class FusedLoraAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = False) -> None:
         """Gradients live in the buckets; they are zeroed (never detached) so the views stay valid."""
         self.sync.zero_grad()
+        if self.extra_optimizer is not None:
+            self.extra_optimizer.zero_grad(set_to_none=True)
 
     def state_dict(self):
         sd = super().state_dict()
         sd["b2q_flat"] = {"step": self._step, "m": [t.clone() for t in self.mflat], "v": [t.clone() for t in self.vflat]}
+        if self.extra_optimizer is not None:
+            sd["b2q_extra"] = self.extra_optimizer.state_dict()
         return sd
 
     def load_state_dict(self, state_dict):
         flat = state_dict.get("b2q_flat")
-        super().load_state_dict({k: v for k, v in state_dict.items() if k != "b2q_flat"})
+        if self.extra_optimizer is not None and "b2q_extra" in state_dict:
+            self.extra_optimizer.load_state_dict(state_dict["b2q_extra"])
+        super().load_state_dict({k: v for k, v in state_dict.items() if k not in ("b2q_flat", "b2q_extra")})
         if flat is not None:
             self._step = int(flat["step"])
             for dst, src in zip(self.mflat, flat["m"]):

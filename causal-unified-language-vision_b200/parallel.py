@@ -13,18 +13,28 @@ Design (one process per GPU, weights replicated, batch sharded):
     REVERSE forward order (the order backward produces them); ``param.grad`` is that view;
   * the backward kernels (``b2q_lora_grads``) write dA / dB straight into the views -- no
     autograd accumulation pass, no flatten / unflatten copies;
-  * ``overlap=True``: when the last gradient of a bucket has been produced an event is recorded on the
+  * ``overlap=True`` (default): when the last gradient of a bucket has been produced an event is recorded on the
     compute stream, the comm stream waits on it and issues ONE ``all_reduce`` for the bucket
     (NCCL over NVLink 5 / NVSwitch; ``ReduceOp.AVG``), overlapping the remaining backward, and
     ``finish()`` makes the compute stream wait for the comm stream before the optimizer step;
-  * ``overlap=False`` (default since the end of round 1, see DESIGN.md "open issue"): ``finish()`` issues
-    the all-reduces of all buckets on the compute stream -- 360 MB per step, < 1 ms on NVLink.
+  * ``overlap=False`` (``B2Q_GRAD_OVERLAP=0``): ``finish()`` issues the all-reduces of all buckets on the compute
+    stream -- 360 MB per step, < 1 ms on NVLink;
+  * every rank issues exactly one all-reduce per bucket per step, in bucket order, whatever subset of modules ran:
+    a bucket is launched early only when all buckets before it have been launched, and ``finish()`` launches the
+    rest (a module skipped on one rank -- data-dependent branch, text-only batch -- can therefore neither leave a
+    bucket unreduced nor reorder the collectives between ranks);
+  * trainable parameters that are NOT LoRA weights (the reference also trains ``multi_modal_projector``,
+    /root/reference/cullavo/load_cullavo.py:128-130) are passed as ``extra_params``: autograd produces their ``.grad``
+    as usual and ``finish()`` mean-reduces them in one flat fp32 all-reduce.
+Gradient accumulation (``accel.accumulate``, /root/reference/trainer/default_trainer.py:167): call ``begin_step()``
+ONCE per optimizer step, set ``sync.defer = True`` for all but the last micro-batch (the kernels then accumulate into
+the buckets and nothing is reduced) and ``False`` for the last one.
 The same class runs on CPU tensors with the ``gloo`` backend (SUM then divide) for tests.
 
 ``backend="b2q"`` (or ``B2Q_COMM_BACKEND=b2q``) issues the bucket all-reduces through the library's own C-ABI
 communicator (``b2q_comm_*`` in include/b2q.h: NCCL resolved with dlopen, the same entry points a host without a torch
 process group would bind) instead of ``torch.distributed``; the unique id travels over the existing process group.
-Compiled and exported, default off: it has not been exercised on hardware yet.
+Default off.
 """
 from __future__ import annotations
 
@@ -50,30 +60,31 @@ class GradSink:
             self._on_ready()
 
 
-@dataclass
+@dataclass(eq=False)
 class _Bucket:
     flat: torch.Tensor
     members: List[int] = field(default_factory=list)  # slot ids
     offsets: List[int] = field(default_factory=list)  # element offset of every member inside `flat`
     pending: int = 0
-    work: object = None
+    launched: bool = False
 
 
 class GradSync:
     def __init__(self, modules: Sequence, adapter_name: str, process_group=None, bucket_bytes: int = 64 << 20,
                  grad_dtype: torch.dtype = torch.bfloat16, install: bool = True, overlap: Optional[bool] = None,
-                 backend: Optional[str] = None):
+                 backend: Optional[str] = None, extra_params: Sequence = ()):
         """``modules``: the LoRA-wrapped linears in FORWARD order (``LoraLinear4bit`` or anything with
-        ``lora_A[adapter].weight`` / ``lora_B[adapter].weight``)."""
-        # overlap=True: a bucket's all-reduce is issued on a side stream as soon as its last gradient kernel is enqueued
-        # and runs concurrently with the rest of backward.  overlap=False (default, B2Q_GRAD_OVERLAP=1 flips it): all
-        # buckets are reduced on the compute stream at finish().  The exchange is 360 MB per 460 ms step (< 1 ms on
-        # NVLink), so serialising it costs ~0.2 %; running NCCL's kernels concurrently with the persistent, all-SM
-        # tcgen05 kernels hung intermittently at 4 GPUs (DESIGN.md, open issue), so the safe order is the default.
+        ``lora_A[adapter].weight`` / ``lora_B[adapter].weight``).  ``extra_params``: other trainable parameters whose
+        autograd-produced ``.grad`` must be mean-reduced with the LoRA gradients."""
+        # overlap=True (default, B2Q_GRAD_OVERLAP=0 flips it): a bucket's all-reduce is issued on a side stream as soon as
+        # its last gradient kernel is enqueued and runs concurrently with the rest of backward -- the schedule of the DDP
+        # reducer this class stands in for.  overlap=False: all buckets are reduced on the compute stream at finish().
         if overlap is None:
             import os
-            overlap = os.environ.get("B2Q_GRAD_OVERLAP", "0") == "1"
+            overlap = os.environ.get("B2Q_GRAD_OVERLAP", "1") == "1"
         self.overlap = bool(overlap)
+        self.extra_params = [p for p in extra_params if p.requires_grad]
+        self._extra_flat = None
         self.adapter = adapter_name
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -117,8 +128,14 @@ class GradSync:
                 off += prm.numel()
                 self._views[(id(mod), which)] = view
                 self._slot_bucket[(id(mod), which)] = len(self.buckets)
-                if prm.dtype == grad_dtype:
-                    prm.grad = view
+                if prm.dtype != grad_dtype:
+                    # the backward kernels write into the bucket views and hand autograd None for A / B: a parameter of
+                    # another dtype would never see a gradient -- PEFT creates LoRA weights in fp32, the reference sweeps
+                    # them to bf16 before it builds the optimizer (/root/reference/cullavo/load_cullavo.py:124-126)
+                    raise TypeError(f"LoRA parameter {which} of {type(mod).__name__} is {prm.dtype}, the gradient buckets "
+                                    f"are {grad_dtype}: convert the adapter weights first (the reference's fp32 -> bf16 "
+                                    "sweep) or pass grad_dtype=")
+                prm.grad = view
             self.buckets.append(b)
         self._written = set()
         self._use_cuda = device.type == "cuda"
@@ -169,34 +186,53 @@ class GradSync:
     def begin_step(self) -> None:
         """Call after ``zero_grad`` / before the first backward of an optimizer step."""
         self._written.clear()
-        self._reduced = False
+        self._next_bucket = 0   # buckets [0, _next_bucket) have been launched this step
         for b in self.buckets:
             b.pending = len(b.members)
-            b.work = None
+            b.launched = False
+        self._extra_reduced = False
+        self._deferred_in_step = False   # a micro-batch was accumulated without reducing: no early launches in this step
         self._done_events = []
 
     def sink_for(self, mod) -> GradSink:
         """Gradient destination for ``mod`` in the coming backward (used by ``LoraLinear4bit.forward``)."""
         key = id(mod)
-        return GradSink(self._views[(key, "A")], self._views[(key, "B")], lambda: key in self._written,
+        return GradSink(self._views[(key, "A")], self._views[(key, "B")], lambda: self._accumulate(key),
                         lambda: self._ready(mod))
+
+    def _accumulate(self, key) -> bool:
+        """Called by backward just before the gradient kernels of a module write: accumulate (second visit) or overwrite?"""
+        for which in ("A", "B"):
+            if self.buckets[self._slot_bucket[(key, which)]].launched:
+                raise RuntimeError(
+                    "a LoRA gradient arrived for a bucket whose all-reduce has already been issued in this step: call "
+                    "GradSync.begin_step() once per optimizer step, and for gradient accumulation set sync.defer = True "
+                    "on all but the last micro-batch (parallel.py docstring)")
+        return key in self._written
 
     def _ready(self, mod) -> None:
         key = id(mod)
         first = key not in self._written
         self._written.add(key)
+        if self.defer:
+            self._deferred_in_step = True
         if not first:
             return
         for which in ("A", "B"):
             bi = self._slot_bucket[(key, which)]
             b = self.buckets[bi]
             b.pending -= 1
-            if b.pending == 0 and self.world > 1 and not self.defer and self.overlap:
-                self._launch(b)
+        if self.world > 1 and not self.defer and not self._deferred_in_step and self.overlap:
+            # in bucket order only: the collective sequence must be the same on every rank
+            while self._next_bucket < len(self.buckets) and self.buckets[self._next_bucket].pending <= 0:
+                self._launch(self.buckets[self._next_bucket])
 
     defer = False  # True while accumulating micro-batches: reduce only on the last one
 
     def _launch(self, b: _Bucket) -> None:
+        assert not b.launched and b is self.buckets[self._next_bucket]
+        b.launched = True
+        self._next_bucket += 1
         if self._comm is not None:
             from . import _lib
             dtype = {torch.bfloat16: 0, torch.float32: 1}[b.flat.dtype]
@@ -221,18 +257,48 @@ class GradSync:
             b.flat.div_(self.world)
 
     def reduce_all(self) -> None:
-        """Reduce every bucket now (after the last micro-batch when ``defer`` was set)."""
+        """Reduce every bucket that has not been reduced in this step, in bucket order (idempotent)."""
         if self.world > 1:
-            for b in self.buckets:
-                self._launch(b)
-            self._reduced = True
+            while self._next_bucket < len(self.buckets):
+                self._launch(self.buckets[self._next_bucket])
+            self._reduce_extra()
+
+    def _reduce_extra(self) -> None:
+        """Mean-reduce the autograd-produced gradients of ``extra_params`` in one flat fp32 all-reduce.  A parameter
+        without a gradient on this rank contributes zeros (and receives the mean), so every rank issues the same call."""
+        if self._extra_reduced or not self.extra_params:
+            return
+        self._extra_reduced = True
+        n = sum(p.numel() for p in self.extra_params)
+        if self._extra_flat is None or self._extra_flat.numel() != n:
+            self._extra_flat = torch.zeros(n, dtype=torch.float32, device=self.extra_params[0].device)
+        flat, off = self._extra_flat, 0
+        for p in self.extra_params:
+            seg = flat[off:off + p.numel()]
+            if p.grad is None:
+                seg.zero_()
+            else:
+                seg.copy_(p.grad.reshape(-1))
+            off += p.numel()
+        if self._use_cuda:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+        off = 0
+        for p in self.extra_params:
+            seg = flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = seg.to(p.dtype)
+            else:
+                p.grad.copy_(seg)
+            off += p.numel()
 
     def finish(self) -> None:
-        """Order the optimizer step after every all-reduce (issuing them here when not overlapping)."""
-        if self.world > 1 and not self.overlap and not self.defer and not self._reduced:
-            for b in self.buckets:
-                self._launch(b)
-            self._reduced = True
+        """Issue every all-reduce that has not been issued in this step and order the optimizer step after all of them.
+        No-op while ``defer`` is set (accumulating micro-batches)."""
+        if self.world > 1 and not self.defer:
+            self.reduce_all()
         if self._use_cuda:
             cur = torch.cuda.current_stream(self.device)
             for ev in self._done_events:

@@ -93,3 +93,109 @@ def test_two_rank_allreduce_mean_gloo():
     for r in (0, 1):
         for i, (a, b) in enumerate(res[r][0]):
             assert abs(a - 1.5 * (i + 1)) < 1e-6 and abs(b - 15.0 * (i + 1)) < 1e-6
+
+
+def test_parameter_dtype_must_match_the_buckets():
+    """PEFT creates LoRA weights in fp32; with bf16 buckets such a parameter would never see a gradient (the kernels write
+    into the bucket views and autograd gets None) -- GradSync must refuse instead of training nothing."""
+    par = importlib.import_module("causal-unified-language-vision_b200.parallel")
+    with pytest.raises(TypeError, match="fp32 -> bf16"):
+        par.GradSync(_mods(), "a", grad_dtype=torch.bfloat16)
+
+
+def test_write_after_launch_is_refused_and_accumulation_defers():
+    par = importlib.import_module("causal-unified-language-vision_b200.parallel")
+    mods = _mods()
+    gs = par.GradSync(mods, "a", bucket_bytes=3000, grad_dtype=torch.float32, overlap=True)
+    gs.world = 2                       # pretend: exercise the launch bookkeeping without a process group
+    launched = []
+    gs._launch_real = gs._launch
+
+    def fake_launch(b):                # record instead of calling a collective
+        assert b is gs.buckets[gs._next_bucket]
+        b.launched = True
+        gs._next_bucket += 1
+        launched.append([id(x) for x in gs.buckets].index(id(b)))
+    gs._launch = fake_launch
+    gs._reduce_extra = lambda: None
+    # micro-batch 1 of 2: nothing may be reduced
+    gs.begin_step()
+    gs.defer = True
+    for m in reversed(mods):
+        s = gs.sink_for(m)
+        assert not s.accumulate()
+        s.ready()
+    gs.finish()
+    assert launched == []
+    # micro-batch 2: kernels accumulate, still no early launch (a bucket is complete only after ALL its modules re-ran)
+    gs.defer = False
+    for m in reversed(mods):
+        s = gs.sink_for(m)
+        assert s.accumulate()
+        s.ready()
+        assert launched == []
+    gs.finish()
+    assert launched == list(range(len(gs.buckets)))
+    # a gradient that arrives after its bucket went out is an error, not a silent overwrite of a buffer in flight
+    with pytest.raises(RuntimeError, match="begin_step"):
+        gs.sink_for(mods[0]).accumulate()
+    # next step, one module skipped: early launches stop at the first incomplete bucket, finish() sends the rest in order
+    launched.clear()
+    gs.begin_step()
+    for m in reversed(mods[1:]):
+        s = gs.sink_for(m)
+        s.accumulate()
+        s.ready()
+    early = list(launched)
+    gs.finish()
+    assert launched == list(range(len(gs.buckets))) and len(early) < len(gs.buckets)
+    assert early == list(range(len(early)))
+
+
+def _worker_skip_and_extra(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = importlib.import_module("causal-unified-language-vision_b200.parallel")
+    mods = _mods()
+    torch.manual_seed(1)
+    proj = nn.Linear(4, 3)             # a non-LoRA trainable module (the reference's multi_modal_projector)
+    frozen = nn.Linear(2, 2).requires_grad_(False)
+    gs = par.GradSync(mods, "a", bucket_bytes=3000, grad_dtype=torch.float32, overlap=True,
+                      extra_params=list(proj.parameters()) + list(frozen.parameters()))
+    assert len(gs.extra_params) == 2
+    gs.zero_grad()
+    for i, m in enumerate(reversed(mods)):
+        if rank == 1 and i == 1:
+            continue                    # rank 1 never runs this module (data-dependent branch): must neither hang nor skip
+        s = gs.sink_for(m)
+        s.accumulate()
+        s.dA.fill_(float(rank + 1))
+        s.dB.fill_(float(rank + 1))
+        s.ready()
+    proj.weight.grad = torch.full_like(proj.weight, float(rank + 1))   # autograd's job; bias has no grad on rank 1
+    if rank == 0:
+        proj.bias.grad = torch.full_like(proj.bias, 4.0)
+    gs.finish()
+    out = [float(m.lora_A["a"].weight.grad.mean()) for m in reversed(mods)]
+    q.put((rank, (out, float(proj.weight.grad.mean()), float(proj.bias.grad.mean()))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_skipped_module_and_extra_params_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_skip_and_extra, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert res[0] == res[1]
+    lora, w, b = res[0]
+    assert lora == [1.5, 0.5, 1.5]      # skipped on rank 1: mean of (1, 0)
+    assert w == 1.5 and b == 2.0        # extra parameters: mean over ranks, a missing gradient counts as zero
