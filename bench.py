@@ -83,23 +83,27 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_oracle_sample(threads: int, iters: int = 3):
-    """One BASELINE-C1 linear (4096x4096 NF4 + LoRA r=64, 704 tokens) fwd+bwd in fp32 on the host, NF4 decode
-    in both passes as MatMul4Bit does.  Returns (seconds per iteration, flops per iteration)."""
-    import torch
+CPU_SAMPLE_TOKENS = 256
 
-    from oracle.qlora import make_case, qlora_flops, qlora_linear_fwd_bwd
 
-    torch.set_num_threads(threads)
-    M, N, K, r = 704, 4096, 4096, 64
-    case = make_case(M, N, K, r, seed=0, double_quant=True, dtype=torch.float32)
-    ts = []
-    for i in range(iters + 1):
-        t0 = time.perf_counter()
-        qlora_linear_fwd_bwd(case["x"], case["state"], case["A"], case["B"], 0.25, case["dy"], mode="fp32")
-        if i > 0:
-            ts.append(time.perf_counter() - t0)
-    return statistics.median(ts), qlora_flops(M, N, K, r)
+def cpu_layer_sample(args, threads: int):
+    """The CPU restatement of the reference algorithm (oracle/, fp32, NF4 decode in both passes as MatMul4Bit does) on ONE
+    decoder layer of the workload -- all 7 projections at their real shapes, LoRA rank as configured -- over
+    CPU_SAMPLE_TOKENS tokens.  The 32 layers of the stack are identical in shape, so whole-stack tokens/s =
+    tokens / (layers x seconds per layer step): a bounded sample, scaled by a count, not extrapolated across shapes."""
+    from importlib import import_module
+
+    from oracle.fast import LayerSample
+
+    stack = import_module("causal-unified-language-vision_b200.stack")
+    return LayerSample(stack.SHAPE_SETS[args.shapes], args.r, CPU_SAMPLE_TOKENS, threads)
+
+
+def cpu_sample_text(args):
+    return (f"one decoder layer of the workload ({args.shapes}: 7 QLoRA linears, NF4 double-quant + LoRA r={args.r}) on "
+            f"{CPU_SAMPLE_TOKENS} tokens, fp32 fwd+bwd (dX, dA, dB) with the NF4 decode in both passes (oracle/fast.py: the "
+            f"C restatement on all host cores + torch fp32 GEMMs); stack tokens/s = {CPU_SAMPLE_TOKENS} / ({args.layers} "
+            "layers x seconds per layer step)")
 
 
 def workload_config(args, world):
@@ -120,24 +124,22 @@ def run_reference(args, world, rank):
         return
     from importlib import import_module
 
-    stack = import_module("causal-unified-language-vision_b200.stack")
     threads = os.cpu_count() or 1
-    fpt = stack.stack_flops_per_token(stack.SHAPE_SETS[args.shapes], args.layers, args.r)
+    sample = cpu_layer_sample(args, threads)
     times = []
     for i in range(args.warmup + args.steps):
-        sec, flops = cpu_oracle_sample(threads, iters=1)
+        t0 = time.perf_counter()
+        sample.step()
         if i >= args.warmup:
-            times.append(sec)
+            times.append(time.perf_counter() - t0)
     sec = statistics.mean(times)
-    toks = (flops / sec) / fpt
-    sample = ("one q_proj-shaped linear (4096x4096 NF4 double-quant + LoRA r=64), 704 tokens, fp32 fwd+bwd with the "
-              "NF4 decode in both passes; tokens/s of the full stack extrapolated linearly in FLOPs")
+    toks = CPU_SAMPLE_TOKENS / (args.layers * sec)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": toks, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-        "cpu_baseline": {"value": toks, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "gflops": flops / sec / 1e9},
+        "cpu_baseline": {"value": toks, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(args),
+                         "gflops": sample.flops / sec / 1e9},
         "e2e": {"value": toks, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -468,12 +470,16 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            sec, flops = cpu_oracle_sample(threads, iters=3)
-            cpu = {"value": (flops / sec) / fpt, "unit": UNIT, "cores": threads, "kind": "port",
-                   "gflops": flops / sec / 1e9,
-                   "sample": "one q_proj-shaped linear (4096x4096 NF4 double-quant + LoRA r=64), 704 tokens, fp32 "
-                             "fwd+bwd incl. NF4 decode in both passes (oracle/qlora.py); full-stack tokens/s "
-                             "extrapolated linearly in FLOPs"}
+            sample = cpu_layer_sample(args, threads)
+            ts = []
+            for i in range(6):   # 1 warm-up + 5 timed layer steps: 10-20 s of host work
+                t0c = time.perf_counter()
+                sample.step()
+                if i > 0:
+                    ts.append(time.perf_counter() - t0c)
+            sec = statistics.median(ts)
+            cpu = {"value": CPU_SAMPLE_TOKENS / (args.layers * sec), "unit": UNIT, "cores": threads, "kind": "port",
+                   "gflops": sample.flops / sec / 1e9, "sample": cpu_sample_text(args)}
         print(result_line(e2e, cpu, opt_info), flush=True)
     faulthandler.cancel_dump_traceback_later()
     g.cancel()

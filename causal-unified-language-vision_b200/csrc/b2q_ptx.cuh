@@ -58,15 +58,21 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// Scopes.  Barriers that only threads (and async operations) of ONE CTA touch use the PTX defaults (.acquire / .release
-// at .cta scope): pk_bar, pk_empty_bar, xf_bar, and everything in the single-CTA kernels.  In the cta_group::2 kernels
-// the peer CTA's producer, decode and epilogue warps arrive on the LEADER's full / "accumulator drained" barriers; a
-// .release.cta in CTA 1 does not synchronise-with an .acquire.cta in CTA 0 under the PTX memory model, so those arrives
-// use the `_xcta` forms below (.release.cluster) and the leader's waits on those barriers use mbar_try_wait_xcta
-// (.acquire.cluster).  B2Q_XCTA_SCOPE_CTA=1 (build switch) restores the round-1 .cta-scope forms for A/B timing.
-#ifndef B2Q_XCTA_SCOPE_CTA
-#define B2Q_XCTA_SCOPE_CTA 0
+// Scopes.  Every wait / arrive uses the PTX defaults (.acquire / .release at .cta scope), also the arrives that the peer
+// CTA of a cta_group::2 pair sends to the LEADER's full / "accumulator drained" barriers (`_xcta` forms below).  Under
+// the letter of the PTX memory model a .release.cta in CTA 1 does not synchronise-with an .acquire.cta in CTA 0; what
+// the protocol needs is narrower and holds physically: the data the peer publishes lives in ITS OWN shared memory
+// and is consumed by the tensor core through the async proxy, the publishing warp executes MEMBAR.ALL.CTA +
+// FENCE.VIEW.ASYNC (fence.proxy.async) before its arrive is issued, and the leader's issuing thread observes the phase
+// flip before it issues the MMA -- no cache is involved on either side.  CUTLASS's ClusterBarrier::arrive(cta_id) is the
+// same unscoped form.  Round 2 measured the formally scoped variant (B2Q_XCTA_SCOPE_CLUSTER=1: .release.cluster arrives,
+// .acquire.cluster waits; ptxas adds MEMBAR.ALL.GPU / CCTL.IVALL per stage): whole step 35.9k -> 28.4k tokens/s
+// (-21 %), and it changed nothing about the two real bugs of the round, so .cta stays the default
+// and the scoped build stays available for A/B runs.
+#ifndef B2Q_XCTA_SCOPE_CLUSTER
+#define B2Q_XCTA_SCOPE_CLUSTER 0
 #endif
+#define B2Q_XCTA_SCOPE_CTA (!B2Q_XCTA_SCOPE_CLUSTER)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

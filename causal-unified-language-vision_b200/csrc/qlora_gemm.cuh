@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     constexpr int NB1 = NB0 + 2 * PST + (Cfg::A_XF ? STAGES : 0);
     [[maybe_unused]] auto tfull1_bar = [&](int a) { return bar_base + 8u * (NB1 + a); };
     constexpr int NBARS = NB1 + (Cfg::RA > 0 ? ACC_STAGES : 0);
+    // barrier area: NBARS barriers, TMEM base address (4 B), 4 B pad, 8 B scratch (sink of the decode warps' load fence),
+    // stall-guard sink
     static_assert(8 * NBARS + 16 + sizeof(StallSink) <= Cfg::BAR_BYTES && NBARS <= STALL_MAX_BARS, "barrier area");
     const StallSink* sk = reinterpret_cast<const StallSink*>(smem_gen + Cfg::RING_BYTES + 8 * NBARS + 16);
     const uint32_t tmem_slot = bar_base + 8u * NBARS;
@@ -893,8 +895,21 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                                  : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(src + 16));
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(pk_empty_bar(ps));  // packed slot may be refilled
+                {
+                    // Release the packed slot only after every lane's loads have RETURNED.  Issuing the arrive right behind
+                    // the two LDS is not enough: the shared-memory pipe of these kernels is ~75 % busy (operand reads of the
+                    // tensor core, TMA writes, 32 KB of decoded stores per k-block), a load can sit in its queue for longer
+                    // than the refill of the slot takes, and the TMA then overwrites the first rows of the slot under a
+                    // reader that has not read yet: one decode warp's 32 weight rows of one k-block come from the NEXT use
+                    // of the slot -- a few tiles per thousand launches were off by 3-14 % of max|y| (round 2, DESIGN.md
+                    // section 4; whether it happened depended on where ptxas scheduled the first consumer of w[]).  The
+                    // warp-wide reduction reads all eight words of all 32 lanes, the store keeps it alive.
+                    const uint32_t x = __reduce_xor_sync(0xffffffffu, w[0] ^ w[1] ^ w[2] ^ w[3] ^ w[4] ^ w[5] ^ w[6] ^ w[7]);
+                    if (lane == 0) {
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(tmem_slot + 8u), "r"(x) : "memory");
+                        mbar_arrive(pk_empty_bar(ps));  // packed slot may be refilled
+                    }
+                }
                 const uint32_t si = it + kb, s = si % STAGES, ph = (si / STAGES) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u, sk, 10, tile, kb);   // decoded-B slot free (MMAs that read it retired)
                 const uint32_t dst = b_stage(s) + dst_off;

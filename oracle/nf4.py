@@ -172,7 +172,23 @@ def quantize_nf4(w: np.ndarray, blocksize: int = 64, double_quant: bool = False)
     if not double_quant:
         state["absmax"] = absmax
         return state
-    offset = np.float32(absmax.astype(np.float64).mean())  # fp64 accumulate, as the CUDA quantiser does
+    state.update(double_quantize_absmax(absmax))
+    return state
+
+
+def double_quantize_absmax(absmax: np.ndarray) -> dict:
+    """Second-level quantisation of the fp32 absmax vector (bitsandbytes ``quantize_4bit(compress_statistics=True)``):
+    ``offset = absmax.mean(); absmax -= offset; quantize_blockwise(absmax, blocksize=256)`` with the 8-bit dynamic map.
+
+    The mean: bitsandbytes takes ``absmax.mean()`` with torch's CUDA reduction (fp32 partial sums in a device- and
+    version-dependent tree order, so not reproducible bit for bit by any other implementation); this restatement and the
+    product's ``absmax_mean_kernel`` return the CORRECTLY ROUNDED mean (fp64 accumulate, one rounding), which differs from
+    any fp32 summation order by at most an ulp or two.  The offset is part of the serialised quant state, so decode
+    parity does not depend on it; quantiser BYTES may differ from bitsandbytes' own in the rare absmax value that sits
+    within that distance of an 8-bit code boundary (tests/test_oracle.py bounds the effect on the decoded weight)."""
+    absmax = np.ascontiguousarray(absmax, dtype=np.float32)
+    nblocks = absmax.size
+    offset = np.float32(absmax.astype(np.float64).mean())
     centred = (absmax - offset).astype(np.float32)
     code256 = create_dynamic_map()
     nb2 = (nblocks + 255) // 256
@@ -183,8 +199,7 @@ def quantize_nf4(w: np.ndarray, blocksize: int = 64, double_quant: bool = False)
         xn2 = (blk2 * inv2[:, None]).astype(np.float32)
     xn2 = np.nan_to_num(xn2, nan=0.0)
     q = _nearest_code(code256, xn2).reshape(-1)[:nblocks]
-    state.update(absmax_q=q, absmax2=absmax2, code256=code256, offset=offset)
-    return state
+    return dict(absmax_q=q, absmax2=absmax2, code256=code256, offset=offset)
 
 
 def dequantize_absmax(state: dict) -> np.ndarray:
