@@ -311,17 +311,23 @@ def simulate_two_sets(num_tiles, kb_total, seed, stages=5):
     assert all(acc_drained.get((t, 0)) for t in range(num_tiles))
 
 
-def simulate_transform(num_tiles, kb_total, seed, stages=6, groups=4):
+def simulate_transform(num_tiles, kb_total, seed, stages=6, groups=4, guard=True):
     """The A-operand transform kernels (LoRA dropout in shared memory): `groups` transform groups take ring positions in
     turn (position si belongs to group si % groups), wait for the TMA data with the parity of (si / stages), mask the
-    tile in place and arrive on the stage's "transformed" barrier, which is what the UMMA issuer waits for."""
+    tile in place and arrive on the stage's "transformed" barrier, which is what the UMMA issuer waits for.
+
+    TMA loads are asynchronous and complete in ANY order (round 2: the model of round 1 completed them in issue order
+    and therefore could not see the stall it was written to exclude).  `guard=True` is the kernel as fixed in round 2: a
+    group first waits for the previous use of the stage to be released (empty barrier), which makes its parity wait on
+    the full barrier exact.  `guard=False` is the round-1 protocol; run_all() checks that the model catches it."""
     rng = random.Random(seed)
     full = [Bar(1) for _ in range(stages)]
     xf = [Bar(1) for _ in range(stages)]        # one arrive per warp of the owning group (modelled as one)
     empty = [Bar(1) for _ in range(stages)]
     stage_content, stage_masked = [None] * stages, [False] * stages
     pipe = []
-    log = {"issuer_done": False, "mmas": 0}
+    inflight = []                               # TMA loads issued and not yet landed: (stage, tile, kb)
+    log = {"issuer_done": False, "mmas": 0, "producer_done": False}
 
     def wait(bar, parity, intended):
         while not bar.passes(parity):
@@ -334,13 +340,26 @@ def simulate_transform(num_tiles, kb_total, seed, stages=6, groups=4):
             for kb in range(kb_total):
                 if use[s] > 0:
                     yield from wait(empty[s], ph ^ 1, use[s] - 1)
-                stage_content[s], stage_masked[s] = (tile, kb), False
+                inflight.append((s, tile, kb))
                 yield "step"
-                full[s].arrive()
                 use[s] += 1
                 s += 1
                 if s == stages:
                     s, ph = 0, ph ^ 1
+        log["producer_done"] = True
+
+    def tma():                                   # lands the in-flight loads in random order
+        while not log["producer_done"] or inflight:
+            if not inflight:
+                yield "blocked"
+                continue
+            if rng.random() < 0.7:              # slow memory: loads stay in flight for a while
+                yield "step"
+                continue
+            st, tile, kb = inflight.pop(rng.randrange(len(inflight)))
+            stage_content[st], stage_masked[st] = (tile, kb), False
+            full[st].arrive()
+            yield "step"
 
     def group(g):
         it = 0
@@ -349,6 +368,8 @@ def simulate_transform(num_tiles, kb_total, seed, stages=6, groups=4):
             while kb < kb_total:
                 si = it + kb
                 st, ph = si % stages, (si // stages) & 1
+                if guard and si >= stages:
+                    yield from wait(empty[st], ph ^ 1, si // stages - 1)
                 yield from wait(full[st], ph, si // stages)
                 assert stage_content[st] == (tile, kb) and not stage_masked[st]
                 yield "step"
@@ -385,7 +406,7 @@ def simulate_transform(num_tiles, kb_total, seed, stages=6, groups=4):
                 log["mmas"] += 1
             yield "step"
 
-    agents = {"producer": producer(), "issuer": issuer(), "pipe": tensor_pipe()}
+    agents = {"producer": producer(), "tma": tma(), "issuer": issuer(), "pipe": tensor_pipe()}
     agents.update({f"xf{g}": group(g) for g in range(groups)})
     blocked_rounds = 0
     while agents:
@@ -402,12 +423,17 @@ def simulate_transform(num_tiles, kb_total, seed, stages=6, groups=4):
     assert log["mmas"] == num_tiles * kb_total
 
 
-def simulate_decode(num_tiles, kb_main, kb_tail, seed, stages=4, pst=4, ng=2):
+def simulate_decode(num_tiles, kb_main, kb_tail, seed, stages=4, pst=4, ng=2, guard=True, fence_reads=True):
     """The decode kernels' main loop: operand ring (A by TMA; B decoded for main k-blocks, by TMA for the LoRA tail
     k-blocks), an independent packed-NF4 ring of depth `pst`, and `ng` decode groups -- group g owns the operand-ring
     positions si with si % ng == g, reads packed position pi = (main k-blocks so far) and releases it, waits for the
     operand slot, writes the decoded tile and arrives on the stage's full barrier; for tail k-blocks the owner only
-    arrives."""
+    arrives.
+
+    Round 2: packed-ring loads land in any order, and a group's READ of a packed slot is asynchronous too (issued, then
+    returned some steps later).  `guard` = wait for the previous use of the packed slot to be released before the parity
+    wait on its "landed" barrier (the reader of a slot alternates between the groups at tile boundaries when kb_tail is
+    odd).  `fence_reads` = release the slot only after the read has returned.  Both False is the round-1 kernel."""
     rng = random.Random(seed)
     kb_total = kb_main + kb_tail
     full = [Bar(2) for _ in range(stages)]      # TMA producer + the owning decode group
@@ -416,7 +442,8 @@ def simulate_decode(num_tiles, kb_main, kb_tail, seed, stages=4, pst=4, ng=2):
     pk_empty = [Bar(1) for _ in range(pst)]
     a_content, b_content, p_content = [None] * stages, [None] * stages, [None] * pst
     pipe = []
-    log = {"issuer_done": False, "mmas": 0}
+    p_inflight = []                             # packed loads issued and not yet landed: (slot, tile, kb)
+    log = {"issuer_done": False, "mmas": 0, "packed_done": False}
 
     def wait(bar, parity, intended):
         while not bar.passes(parity):
@@ -445,13 +472,26 @@ def simulate_decode(num_tiles, kb_main, kb_tail, seed, stages=4, pst=4, ng=2):
             for kb in range(kb_main):
                 if use[ps] > 0:
                     yield from wait(pk_empty[ps], pph ^ 1, use[ps] - 1)
-                p_content[ps] = (tile, kb)
+                p_inflight.append((ps, tile, kb))
                 yield "step"
-                pk[ps].arrive()
                 use[ps] += 1
                 ps += 1
                 if ps == pst:
                     ps, pph = 0, pph ^ 1
+        log["packed_done"] = True
+
+    def packed_tma():
+        while not log["packed_done"] or p_inflight:
+            if not p_inflight:
+                yield "blocked"
+                continue
+            if rng.random() < 0.7:              # slow memory: loads stay in flight for a while
+                yield "step"
+                continue
+            ps, tile, kb = p_inflight.pop(rng.randrange(len(p_inflight)))
+            p_content[ps] = (tile, kb)
+            pk[ps].arrive()
+            yield "step"
 
     def group(g):
         it = pit = 0
@@ -460,10 +500,18 @@ def simulate_decode(num_tiles, kb_main, kb_tail, seed, stages=4, pst=4, ng=2):
             while kb < kb_main:
                 pi = pit + kb
                 ps, pph = pi % pst, (pi // pst) & 1
+                if guard and pi >= pst:
+                    yield from wait(pk_empty[ps], pph ^ 1, pi // pst - 1)
                 yield from wait(pk[ps], pph, pi // pst)
-                assert p_content[ps] == (tile, kb), "decode read a packed slot holding another k-block"
-                yield "step"
-                pk_empty[ps].arrive()
+                if fence_reads:                 # the load returns (its value is consumed) before the slot is released
+                    yield "step"
+                    assert p_content[ps] == (tile, kb), "decode read a packed slot holding another k-block"
+                    pk_empty[ps].arrive()
+                else:                           # round 1: released as soon as the load is issued; it returns later
+                    pk_empty[ps].arrive()
+                    for _ in range(rng.randrange(0, 12)):
+                        yield "step"
+                    assert p_content[ps] == (tile, kb), "decode read a packed slot holding another k-block"
                 si = it + kb
                 st, ph = si % stages, (si // stages) & 1
                 if si >= stages:
@@ -511,7 +559,8 @@ def simulate_decode(num_tiles, kb_main, kb_tail, seed, stages=4, pst=4, ng=2):
                 log["mmas"] += 1
             yield "step"
 
-    agents = {"producer": producer(), "packed": packed_producer(), "issuer": issuer(), "pipe": tensor_pipe()}
+    agents = {"producer": producer(), "packed": packed_producer(), "packed_tma": packed_tma(), "issuer": issuer(),
+              "pipe": tensor_pipe()}
     agents.update({f"dec{g}": group(g) for g in range(ng)})
     blocked_rounds = 0
     while agents:
@@ -549,6 +598,18 @@ def run_all(seeds=12):
             for tiles in (1, 2, 3, 5):
                 for seed in range(max(1, seeds // 3)):
                     simulate_decode(tiles, kb_main, kb_tail, seed)
+    # mutation checks (round 2): the round-1 protocols must FAIL in the model now that loads land out of order
+    def fails(fn, *a, **k):
+        bad = 0
+        for seed in range(300):
+            try:
+                fn(*a, seed, **k)
+            except (AssertionError, Deadlock):
+                bad += 1
+        return bad
+    assert fails(simulate_transform, 2, 13, guard=False) > 0, "model does not see the transform-group phase alias"
+    assert fails(simulate_decode, 3, 5, 1, guard=False) > 0, "model does not see the packed-ring alias at tile boundaries"
+    assert fails(simulate_decode, 2, 8, 0, fence_reads=False) > 0, "model does not see the early release of a packed slot"
     return n
 
 
