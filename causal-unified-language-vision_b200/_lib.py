@@ -48,7 +48,6 @@ SIGNATURES = {
     "b2q_absmax_double_quant": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2q_gemv_4bit": (c_int, [c_void_p, ct.POINTER(NF4Weight), c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2q_dropout_mask": (c_int, [c_void_p, c_i64, c_u64, c_float, c_void_p]),
-    "b2q_dropout_mask_bits": (c_int, [c_void_p, c_i64, c_u64, c_float, c_void_p]),
     "b2q_dropout_apply": (c_int, [c_void_p, c_void_p, c_i64, c_u64, c_float, c_void_p]),
     "b2q_dropout_bwd_add": (c_int, [c_void_p, c_void_p, c_i64, c_u64, c_float, c_void_p]),
     "b2q_lora_down": (c_int, [c_void_p, c_void_p, c_float, c_u64, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -76,7 +75,6 @@ SIGNATURES = {
     "b2q_set_variant": (c_int, [c_int, c_int]),
     "b2q_debug_set_trace": (c_int, [c_void_p, c_int]),
     "b2q_debug_set_prefetch": (c_int, [c_int]),
-    "b2q_debug_set_mask_bits": (c_int, [c_void_p, c_i64]),
     "b2q_debug_stall_count": (c_int, []),
     "b2q_debug_stall_report": (c_int, [ct.c_char_p, c_size_t]),
     "b2q_debug_stall_selftest": (c_int, [c_void_p]),

@@ -53,43 +53,6 @@ __host__ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, u
     const uint32_t r = ((idx & 1ull) ? (h >> 16) : h) & 0x7FFFu;
     return r >= (thr2 & 0xFFFFu);
 }
-// Packed form of the same mask (experiment: consumers read bits instead of hashing; B2Q_MASK_BITS=1).  Bit k of byte b is
-// keep(8 b + k).  dropout_bits32 produces the 32 bits of elements [e0, e0 + 32) (e0 a multiple of 32) from 8 hashes.
-__host__ __device__ __forceinline__ uint32_t dropout_bits32(uint32_t seed_lo, uint32_t seed_hi, unsigned long long e0,
-                                                            uint32_t thr2) {
-    const uint32_t thr = thr2 & 0xFFFFu;
-    const uint32_t j0 = static_cast<uint32_t>(e0 >> 2);
-    uint32_t bits = 0;
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-        uint32_t a, b;
-        dropout_hash64(seed_lo, seed_hi, j0 + h, a, b);
-        const uint32_t k = ((a & 0x7FFFu) >= thr ? 1u : 0u) | (((a >> 16) & 0x7FFFu) >= thr ? 2u : 0u) |
-                           ((b & 0x7FFFu) >= thr ? 4u : 0u) | (((b >> 16) & 0x7FFFu) >= thr ? 8u : 0u);
-        bits |= k << (4 * h);
-    }
-    return bits;
-}
-// One mask byte (8 consecutive elements = one 16-byte chunk of bf16) -> the four bf16x2 AND-masks of the chunk's words.
-// Two multiplies move bit i of each nibble to the sign bit of byte i (the partial products never share a bit position,
-// so nothing carries); PRMT in sign-replicate mode then expands byte signs to byte masks, two bytes per element.
-__host__ __device__ __forceinline__ void dropout_byte_to_masks(uint32_t byte, uint32_t (&m)[4]) {
-    const uint32_t x0 = (byte & 0xFu) * 0x10204080u;          // bits 0..3 -> signs of bytes 0..3
-    const uint32_t x1 = ((byte >> 4) & 0xFu) * 0x10204080u;   // bits 4..7
-#ifdef __CUDA_ARCH__
-    asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(m[0]) : "r"(x0));
-    asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(m[1]) : "r"(x0));
-    asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(m[2]) : "r"(x1));
-    asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(m[3]) : "r"(x1));
-#else
-    const uint32_t xs[2] = {x0, x1};
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t x = xs[j >> 1];
-        const int lo = (j & 1) ? 23 : 7, hi = (j & 1) ? 31 : 15;   // sign bits of bytes (0,1) or (2,3)
-        m[j] = (((x >> lo) & 1u) ? 0x0000FFFFu : 0u) | (((x >> hi) & 1u) ? 0xFFFF0000u : 0u);
-    }
-#endif
-}
 // 15-bit threshold round(p * 32768), replicated into both 16-bit halves
 inline uint32_t dropout_threshold(float p) {
     const double t = static_cast<double>(p) * 32768.0 + 0.5;

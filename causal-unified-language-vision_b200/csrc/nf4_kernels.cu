@@ -361,16 +361,6 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__
         mask[i] = dropout_keep(seed, static_cast<unsigned long long>(i), thresh) ? 1 : 0;
 }
 
-// Packed mask (experiment, B2Q_MASK_BITS=1): word w holds keep bits of elements [32 w, 32 w + 32), bit k of byte b is
-// keep(8 b + k).  One thread = one word = 8 hashes.
-__global__ void __launch_bounds__(256) dropout_mask_bits_kernel(uint32_t* __restrict__ bits, long long n_words,
-                                                                unsigned long long seed, uint32_t thresh) {
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; w < n_words; w += stride)
-        bits[w] = dropout_bits32(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
-                                 static_cast<unsigned long long>(w) * 32ull, thresh);
-}
-
 // xd = bf16(x * keep / (1 - p)), 8 elements (16 B) per thread-step.
 __global__ void __launch_bounds__(256) dropout_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ xd,
                                                             long long n_vec, unsigned long long seed,
@@ -522,17 +512,6 @@ extern "C" int b2q_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, float p
     if (n == 0) return 0;
     if (!(p >= 0.f && p < 1.f)) return B2Q_ERR_ARG;
     dropout_mask_kernel<<<grid_for(n, 256), 256, 0, stream>>>(mask, n, seed, dropout_threshold(p));
-    count_launch();
-    return static_cast<int>(cudaGetLastError());
-}
-
-extern "C" int b2q_dropout_mask_bits(void* bits, int64_t n, uint64_t seed, float p, cudaStream_t stream) {
-    if (n == 0) return 0;
-    if (bits == nullptr || (reinterpret_cast<uintptr_t>(bits) & 15) != 0) return B2Q_ERR_ARG;
-    if (n % 32 != 0) return B2Q_ERR_SHAPE;
-    if (!(p >= 0.f && p < 1.f)) return B2Q_ERR_ARG;
-    dropout_mask_bits_kernel<<<grid_for(n / 32, 256), 256, 0, stream>>>(static_cast<uint32_t*>(bits), n / 32, seed,
-                                                                       dropout_threshold(p));
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

@@ -188,8 +188,6 @@ static long long* g_trace = nullptr;   // debug: phase trace buffer for the next
 static int g_trace_tiles = 0;
 static int g_pf_dist = 0;
 static int g_pdl = -1;   // -1: read B2Q_PDL (default off)
-static const uint8_t* g_mask_bits = nullptr;   // experiment: packed dropout mask for the next lora_down / lora_grads calls
-static long long g_mask_bytes = 0;
 
 template <class Cfg>
 static int launch(GemmParams& p, cudaStream_t stream) {
@@ -273,17 +271,11 @@ using FwdV4 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, 1
 using DxV4 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, 1>;
 using FwdV5 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, -1>;
 using DxV5 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, -1>;
-// experiment (variant 6, opt-in): V5 with the UMMA issuer running sub-tile 0 three k-blocks ahead at the start of a tile
-using FwdV6 = GemmCfg<2, 2, 256, false, false, true, EPI_BF16, 4, 2, 4, false, -1, 1, 3>;
-using DxV6 = GemmCfg<2, 2, 256, false, true, true, EPI_BF16, 4, 2, 4, false, -1, 1, 3>;
 
 template <int R> constexpr int skinny_stages() { return 6; }
 template <int R> using DownCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>()>;   // u = x A^T
 template <int R> using DownDropCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>(), 0, 0, true>;   // u = drop(x) A^T
 template <int R> using GradADropCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true>;
-// experiment (b2q_debug_set_mask_bits): the same two kernels reading a packed mask instead of hashing it
-template <int R> using DownDropBitsCfg = GemmCfg<1, 1, R, false, false, false, EPI_BF16, skinny_stages<R>(), 0, 0, true, 0, 1, 0, true>;
-template <int R> using GradADropBitsCfg = GemmCfg<1, 1, R, true, true, false, EPI_F32_PART_T, 6, 0, 0, true, 0, 1, 0, true>;
 // dx += keep * (du A) / (1 - p): masked epilogue, 128-bit vector reductions into dx at the L2 (dropout backward)
 using GemmKNMask = GemmCfg<1, 1, 128, false, true, false, EPI_BF16_MASK, 5, 0, 0, false, -1, 2>;   // two epilogue warp sets
 template <int R> using DuCfg = GemmCfg<1, 1, R, false, true, false, EPI_BF16, skinny_stages<R>()>;      // du = s dy B
@@ -323,15 +315,12 @@ static const char* stall_site_name(uint32_t site) {
         case 4: return "UMMA issuer: accumulator drained (tempty_bar)";
         case 5: return "packed producer: slot free (pk_empty_bar)";
         case 6: return "epilogue: accumulator complete (tfull_bar)";
-        case 7: return "epilogue: sub-tile 1 complete (tfull1_bar)";
         case 8: return "A transform: operand landed (full_bar)";
         case 9: return "decode: packed bytes landed (pk_bar)";
         case 10: return "decode: B stage free (empty_bar)";
         case 11: return "decode, LoRA tail k-block: stage free (empty_bar)";
         case 16: return "A transform: previous use of the stage released (empty_bar)";
         case 17: return "decode: previous use of the packed slot released (pk_empty_bar)";
-        case 12: case 14: return "UMMA issuer (run-ahead): accumulator drained (tempty_bar)";
-        case 13: case 15: return "UMMA issuer (run-ahead): operands ready (full_bar)";
         default: return "?";
     }
 }
@@ -356,12 +345,12 @@ extern "C" int b2q_debug_stall_report(char* out, size_t cap) {
         if (r[0] != STALL_MAGIC) { snprintf(line, sizeof(line), "  [%d] (incomplete)\n", i); t += line; continue; }
         const uint32_t c = r[1];
         snprintf(line, sizeof(line),
-                 "  [%d] cfg 0x%x {CG %u MT %u BN %u A_MN %u B_MN %u B_DEC %u EPI %u STAGES %u A_XF %u STG %s ESETS %u RA %u} "
+                 "  [%d] cfg 0x%x {CG %u MT %u BN %u A_MN %u B_MN %u B_DEC %u EPI %u STAGES %u A_XF %u STG %s ESETS %u} "
                  "cta %u/%u (cluster rank %u, sm %u) thread %u (warp %u) site %u <%s> barrier #%u parity %u tile %d kb %d | "
                  "M %u N %u kb_main %u kb_tail %u splits %u tiles %u\n",
                  i, c, c & 3u, (c >> 2) & 3u, ((c >> 4) & 15u) * 64u, (c >> 8) & 1u, (c >> 9) & 1u, (c >> 10) & 1u,
                  (c >> 11) & 3u, (c >> 13) & 15u, (c >> 17) & 1u, ((c >> 18) & 1u) ? "coal" : ((c >> 19) & 1u) ? "tma" : "row",
-                 ((c >> 20) & 1u) + 1u, (c >> 21) & 7u, r[2], r[13], r[9], r[11], r[3], r[3] >> 5, r[4], stall_site_name(r[4]),
+                 ((c >> 20) & 1u) + 1u, r[2], r[13], r[9], r[11], r[3], r[3] >> 5, r[4], stall_site_name(r[4]),
                  r[5], r[6], static_cast<int>(r[7]), static_cast<int>(r[8]), r[14], r[15], r[16], r[17], r[18], r[19]);
         t += line;
         const uint32_t nb = r[10] < static_cast<uint32_t>(STALL_MAX_BARS) ? r[10] : static_cast<uint32_t>(STALL_MAX_BARS);
@@ -430,12 +419,6 @@ extern "C" int b2q_debug_mbar_probe(uint64_t* out_words, cudaStream_t stream) {
     return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int b2q_debug_set_mask_bits(const void* bits, int64_t bytes) {
-    g_mask_bits = static_cast<const uint8_t*>(bits);
-    g_mask_bytes = bits != nullptr ? static_cast<long long>(bytes) : 0;
-    return 0;
-}
-
 extern "C" int b2q_debug_set_trace(void* buf, int tiles_per_cta) {
     g_trace = static_cast<long long*>(buf);
     g_trace_tiles = tiles_per_cta;
@@ -490,10 +473,6 @@ extern "C" int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void*
         if ((e = map_bf16_out(&p.tmD, y, M, N, N))) return e;
         if ((e = setup(FwdV4::BNC, slab(FwdV4::TILE_M)))) return e;
         return launch<FwdV4>(p, stream);
-    }
-    if (variant == 6) {
-        if ((e = setup(FwdV6::BNC, slab(FwdV6::TILE_M)))) return e;
-        return launch<FwdV6>(p, stream);
     }
     if ((e = setup(FwdV5::BNC, slab(FwdV5::TILE_M)))) return e;
     return launch<FwdV5>(p, stream);
@@ -559,7 +538,6 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
             if ((e = setup(DxV4::BNC, slab(DxV4::TILE_M)))) return e;
             e = launch<DxV4>(p, stream);
             break;
-        case 6: if ((e = setup(DxV6::BNC, slab(DxV6::TILE_M)))) return e; e = launch<DxV6>(p, stream); break;
         default: if ((e = setup(DxV5::BNC, slab(DxV5::TILE_M)))) return e; e = launch<DxV5>(p, stream); break;
     }
     if (e || !masked || mask_first) return e;
@@ -579,12 +557,6 @@ static int lora_down_r(const void* x, const void* lora_A, float scale, uint64_t 
     int e;
     if ((e = map_bf16_kmajor(&p.tmA, x, M, K, 128))) return e;
     if ((e = map_bf16_kmajor(&p.tmB, lora_A, R, K, R))) return e;
-    if (drop_p > 0.f && g_mask_bits != nullptr) {
-        if (g_mask_bytes < static_cast<long long>(M) * K / 8 || g_mask_bytes >= (1ll << 32)) return B2Q_ERR_ARG;
-        p.mask_bits = g_mask_bits;
-        p.mask_bytes = g_mask_bytes;
-        return launch<DownDropBitsCfg<R>>(p, stream);
-    }
     if (drop_p > 0.f) return launch<DownDropCfg<R>>(p, stream);
     return launch<DownCfg<R>>(p, stream);
 }
@@ -648,12 +620,7 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
         p.seed = seed; p.thresh16 = dropout_threshold(drop_p); p.xf_ld = K;
         if ((e = map_bf16_mnmajor(&p.tmA, xd, M, K))) return e;
         if ((e = map_bf16_mnmajor(&p.tmB, du, M, R))) return e;
-        if (drop_p > 0.f && g_mask_bits != nullptr) {
-            if (g_mask_bytes < static_cast<long long>(M) * K / 8 || g_mask_bytes >= (1ll << 32)) return B2Q_ERR_ARG;
-            p.mask_bits = g_mask_bits;
-            p.mask_bytes = g_mask_bytes;
-            e = launch<GradADropBitsCfg<R>>(p, stream);
-        } else if (drop_p > 0.f) e = launch<GradADropCfg<R>>(p, stream); else e = launch<GradACfg<R>>(p, stream);
+        if (drop_p > 0.f) e = launch<GradADropCfg<R>>(p, stream); else e = launch<GradACfg<R>>(p, stream);
         if (e) return e;
         if ((e = b2q_reduce_partials(wa, sa, static_cast<int64_t>(R) * K, 1.0f / (1.0f - drop_p), dA, accumulate,
                                      stream)))

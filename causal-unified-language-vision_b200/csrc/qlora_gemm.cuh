@@ -72,35 +72,19 @@ struct GemmParams {
     long long* trace;
     int trace_tiles;
     int pf_dist;       // L2 prefetch distance of the A operand in k-blocks (0 = off)
-    // experiment (XF_BITS configs): packed LoRA-dropout mask of the activation, bit k of byte b = keep(8 b + k)
-    const uint8_t* mask_bits;
-    long long mask_bytes;   // size of mask_bits (rows of the operand tile past the activation read nothing)
     // stall guard (b2q_ptx.cuh): host-mapped record buffer of the library, or nullptr
     uint32_t* stall_buf;
 };
 
 template <int CG_, int MT_, int BN_, bool A_MN_, bool B_MN_, bool B_DEC_, int EPI_, int STAGES_, int NG_ = 2,
-          int PST_ = 6, bool A_XF_ = false, int STG_ = 0, int ESETS_ = 1, int RA_ = 0, bool XF_BITS_ = false>
+          int PST_ = 6, bool A_XF_ = false, int STG_ = 0, int ESETS_ = 1>
 struct GemmCfg {
-    // XF_BITS (experiment): the A-operand transform reads the packed mask (GemmParams::mask_bits) instead of hashing.
-    static constexpr bool XF_BITS = XF_BITS_;
-    static_assert(!XF_BITS_ || A_XF_, "XF_BITS is a mode of the A-operand transform");
     // configuration id carried by stall records (decoded by b2q_debug_stall_report)
     static constexpr uint32_t ID = static_cast<uint32_t>(CG_) | (static_cast<uint32_t>(MT_) << 2) |
                                    (static_cast<uint32_t>(BN_ / 64) << 4) | (A_MN_ ? 1u << 8 : 0u) | (B_MN_ ? 1u << 9 : 0u) |
                                    (B_DEC_ ? 1u << 10 : 0u) | (static_cast<uint32_t>(EPI_) << 11) |
                                    (static_cast<uint32_t>(STAGES_) << 13) | (A_XF_ ? 1u << 17 : 0u) |
-                                   (STG_ < 0 ? 1u << 18 : 0u) | (STG_ > 0 ? 1u << 19 : 0u) | (ESETS_ == 2 ? 1u << 20 : 0u) |
-                                   (static_cast<uint32_t>(RA_) << 21) | (XF_BITS_ ? 1u << 24 : 0u);
-    // RA > 0 (experiment, MT == 2 with a single accumulator stage): the UMMA issuer reorders the first and the last RA
-    // k-blocks of a tile.  Head: sub-tile 0 of the first RA k-blocks as soon as the epilogue has drained sub-tile 0 of the
-    // previous tile, then sub-tile 1 of the same k-blocks (releasing their operand stages) once sub-tile 1 is drained
-    // too.  Tail: sub-tile 0 of the last RA k-blocks first and a separate "sub-tile 0 complete" commit, so the epilogue
-    // drains sub-tile 0 while the tensor pipe finishes sub-tile 1.  The pipe then idles ~2.9 k instead of ~5.5 k cycles
-    // per 84 k-cycle tile.  Same MMAs, same order per accumulator element: results are bit-identical to RA == 0.
-    static constexpr int RA = RA_;
-    static_assert(RA_ == 0 || (MT_ == 2 && 2 * MT_ * BN_ > 512 && RA_ < STAGES_ && !A_XF_ && STG_ != 0),
-                  "run-ahead: two sub-tiles, one accumulator stage, staged epilogue");
+                                   (STG_ < 0 ? 1u << 18 : 0u) | (STG_ > 0 ? 1u << 19 : 0u) | (ESETS_ == 2 ? 1u << 20 : 0u);
     // ESETS = 2: two sets of four epilogue warps (4-7 and 8-11), one per accumulator stage, for kernels that are all
     // epilogue (one k-block per tile): set e drains the tiles whose sequence number is e (mod 2).
     static constexpr int ESETS = ESETS_;
@@ -204,10 +188,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     auto pk_bar = [&](int s) { return bar_base + 8u * (NB0 + s); };
     auto pk_empty_bar = [&](int s) { return bar_base + 8u * (NB0 + PST + s); };
     auto xf_bar = [&](int s) { return bar_base + 8u * (NB0 + 2 * PST + s); };
-    // RA configs: tfull_bar(a) = "sub-tile 0 complete", tfull1_bar(a) = "sub-tile 1 complete" (see the UMMA issuer)
-    constexpr int NB1 = NB0 + 2 * PST + (Cfg::A_XF ? STAGES : 0);
-    [[maybe_unused]] auto tfull1_bar = [&](int a) { return bar_base + 8u * (NB1 + a); };
-    constexpr int NBARS = NB1 + (Cfg::RA > 0 ? ACC_STAGES : 0);
+    constexpr int NBARS = NB0 + 2 * PST + (Cfg::A_XF ? STAGES : 0);
     // barrier area: NBARS barriers, TMEM base address (4 B), 4 B pad, 8 B scratch (sink of the decode warps' load fence),
     // stall-guard sink
     static_assert(8 * NBARS + 16 + sizeof(StallSink) <= Cfg::BAR_BYTES && NBARS <= STALL_MAX_BARS, "barrier area");
@@ -250,7 +231,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
             mbar_init(pk_empty_bar(s), Cfg::NDW);         // decode warps, once the bytes are in registers
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
-            if constexpr (Cfg::RA > 0) mbar_init(tfull1_bar(a), 1);
             mbar_init(tfull_bar(a), 1);                   // tcgen05.commit
             for (int mt = 0; mt < MT; ++mt) mbar_init(tempty_bar(a, mt), CG * 4);  // one arrive per epilogue warp, both CTAs
         }
@@ -358,142 +338,41 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 long long* tr = (p.trace != nullptr && tseq < p.trace_tiles)
                                     ? p.trace + (static_cast<long long>(blockIdx.x) * p.trace_tiles + tseq) * 8 : nullptr;
                 long long full_wait = 0;
-                if constexpr (Cfg::RA == 0) {
-                    for (int kb = 0; kb < kb_total; ++kb) {
-                        long long w0 = 0;
-                        if (tr != nullptr) {
-                            w0 = clock64();
-                            if (kb == 0) tr[0] = w0;
-                        }
-                        mbar_wait<CG == 2>(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph, sk, 3, tile, kb);
-                        tc_fence_after();
-                        if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
-                        const uint64_t a_base = Cfg::A_MN ? umma_desc_sw128(a_stage(s), 8192, 1024) : umma_desc_sw128(a_stage(s), 16, 1024);
-                        const uint64_t b_base = Cfg::B_MN ? umma_desc_sw128(b_stage(s), 8192, 1024) : umma_desc_sw128(b_stage(s), 16, 1024);
-    #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
-                                if (tr != nullptr && mt == 0) tr[1] = clock64();
-                                mbar_wait<CG == 2>(tempty_bar(as, mt), aph ^ 1u, sk, 4, tile, mt);
-                                tc_fence_after();
-                                if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
-                            }
-                            const uint32_t d_tmem = tmem_base + as * ACC_COLS + mt * BN;
-                            // descriptors of (stage, mt, k) = descriptor of the stage base + a constant in the address field
-                            // (the stage bases are 1024-byte aligned and the offsets stay far below the 14-bit field)
-    #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t adesc = a_base + static_cast<uint64_t>((mt * 16384 + k * (Cfg::A_MN ? 2048 : 32)) >> 4);
-                                const uint64_t bdesc = b_base + static_cast<uint64_t>((k * (Cfg::B_MN ? 2048 : 32)) >> 4);
-                                umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                            }
-                        }
-                        umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
-                        if (kb == kb_total - 1) {
-                            umma_commit<CG>(tfull_bar(as));
-                            if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
-                        }
-                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    long long w0 = 0;
+                    if (tr != nullptr) {
+                        w0 = clock64();
+                        if (kb == 0) tr[0] = w0;
                     }
-                } else {
-                    auto issue_mt = [&](int s_, int mt, int kb) {   // the four k=16 MMAs of (stage s_, sub-tile mt)
-                        const uint64_t a_base = Cfg::A_MN ? umma_desc_sw128(a_stage(s_), 8192, 1024) : umma_desc_sw128(a_stage(s_), 16, 1024);
-                        const uint64_t b_base = Cfg::B_MN ? umma_desc_sw128(b_stage(s_), 8192, 1024) : umma_desc_sw128(b_stage(s_), 16, 1024);
+                    mbar_wait<CG == 2>(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph, sk, 3, tile, kb);
+                    tc_fence_after();
+                    if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
+                    const uint64_t a_base = Cfg::A_MN ? umma_desc_sw128(a_stage(s), 8192, 1024) : umma_desc_sw128(a_stage(s), 16, 1024);
+                    const uint64_t b_base = Cfg::B_MN ? umma_desc_sw128(b_stage(s), 8192, 1024) : umma_desc_sw128(b_stage(s), 16, 1024);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
+                            if (tr != nullptr && mt == 0) tr[1] = clock64();
+                            mbar_wait<CG == 2>(tempty_bar(as, mt), aph ^ 1u, sk, 4, tile, mt);
+                            tc_fence_after();
+                            if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
+                        }
                         const uint32_t d_tmem = tmem_base + as * ACC_COLS + mt * BN;
                         // descriptors of (stage, mt, k) = descriptor of the stage base + a constant in the address field
                         // (the stage bases are 1024-byte aligned and the offsets stay far below the 14-bit field)
-    #pragma unroll
+#pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t adesc = a_base + static_cast<uint64_t>((mt * 16384 + k * (Cfg::A_MN ? 2048 : 32)) >> 4);
                             const uint64_t bdesc = b_base + static_cast<uint64_t>((k * (Cfg::B_MN ? 2048 : 32)) >> 4);
                             umma_ss<CG>(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         }
-                    };
-                    int kb_begin = 0, kb_end = kb_total;
-                    if constexpr (Cfg::RA > 0) {
-                        // Head: sub-tile 0 of k-blocks [0, ra) as soon as ITS accumulator is drained, then sub-tile 1 of the
-                        // same k-blocks once sub-tile 1 is drained too (the operand stages are released in the second pass).
-                        const int ra = kb_total < Cfg::RA ? kb_total : Cfg::RA;
-                        const int rt = (kb_total - ra) < Cfg::RA ? (kb_total - ra) : Cfg::RA;   // tail window, see below
-                        if (tr != nullptr) tr[0] = tr[1] = clock64();
-                        mbar_wait<CG == 2>(tempty_bar(as, 0), aph ^ 1u, sk, 12, tile, 0);
-                        tc_fence_after();
-                        if (tr != nullptr) tr[2] = clock64();
-                        int s2 = s;
-                        for (int kb = 0; kb < ra; ++kb) {
-                            // (ra < STAGES: the window wraps the ring at most once; a wrapped stage is one phase further)
-                            mbar_wait<CG == 2>(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph, sk, 13, tile, kb);
-                            tc_fence_after();
-                            issue_mt(s2, 0, kb);
-                            if (kb == kb_total - 1) umma_commit<CG>(tfull_bar(as));
-                            if (++s2 == STAGES) s2 = 0;
-                        }
-                        mbar_wait<CG == 2>(tempty_bar(as, 1), aph ^ 1u, sk, 14, tile, 1);
-                        tc_fence_after();
-                        if (tr != nullptr) tr[3] = clock64();
-                        for (int kb = 0; kb < ra; ++kb) {
-                            issue_mt(s, 1, kb);
-                            umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
-                            if (kb == kb_total - 1) {
-                                umma_commit<CG>(tfull1_bar(as));
-                                if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
-                            }
-                            if (++s == STAGES) { s = 0; ph ^= 1u; }
-                        }
-                        kb_begin = ra;
-                        kb_end = kb_total - rt;
                     }
-                    for (int kb = kb_begin; kb < kb_end; ++kb) {
-                        long long w0 = 0;
-                        if (tr != nullptr) {
-                            w0 = clock64();
-                            if (kb == 0) tr[0] = w0;
-                        }
-                        mbar_wait<CG == 2>(Cfg::A_XF ? xf_bar(s) : full_bar(s), ph, sk, 3, tile, kb);
-                        tc_fence_after();
-                        if (tr != nullptr && kb >= STAGES) full_wait += clock64() - w0;
-    #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            if (kb == 0) {   // this sub-tile's accumulator has been drained by the epilogue
-                                if (tr != nullptr && mt == 0) tr[1] = clock64();
-                                mbar_wait<CG == 2>(tempty_bar(as, mt), aph ^ 1u, sk, 4, tile, mt);
-                                tc_fence_after();
-                                if (tr != nullptr) tr[2 + (mt > 0)] = clock64();
-                            }
-                            issue_mt(s, mt, kb);
-                            if constexpr (Cfg::RA > 0) {
-                                if (mt == 0 && kb == kb_total - 1) umma_commit<CG>(tfull_bar(as));
-                            }
-                        }
-                        umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
-                        if (kb == kb_total - 1) {
-                            if constexpr (Cfg::RA > 0) umma_commit<CG>(tfull1_bar(as)); else umma_commit<CG>(tfull_bar(as));
-                            if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
-                        }
-                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    umma_commit<CG>(empty_bar(s));            // stage free once these MMAs retire
+                    if (kb == kb_total - 1) {
+                        umma_commit<CG>(tfull_bar(as));
+                        if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
                     }
-                    if constexpr (Cfg::RA > 0) {
-                        // Tail: the last rt k-blocks of sub-tile 0 first, so that the epilogue drains sub-tile 0 while the
-                        // tensor pipe still works on sub-tile 1 of the same k-blocks.
-                        const int rt = kb_total - kb_end;
-                        if (rt > 0) {
-                            int s2 = s;
-                            for (int kb = kb_end; kb < kb_total; ++kb) {
-                                mbar_wait<CG == 2>(full_bar(s2), (s2 < s) ? (ph ^ 1u) : ph, sk, 15, tile, kb);
-                                tc_fence_after();
-                                issue_mt(s2, 0, kb);
-                                if (++s2 == STAGES) s2 = 0;
-                            }
-                            umma_commit<CG>(tfull_bar(as));
-                            for (int kb = kb_end; kb < kb_total; ++kb) {
-                                issue_mt(s, 1, kb);
-                                umma_commit<CG>(empty_bar(s));
-                                if (++s == STAGES) { s = 0; ph ^= 1u; }
-                            }
-                            umma_commit<CG>(tfull1_bar(as));
-                            if (tr != nullptr) { tr[4] = clock64(); tr[7] = full_wait; }
-                        }
-                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
                 if (++as == ACC_STAGES) { as = 0; aph ^= 1u; }
             }
@@ -554,12 +433,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
 #pragma unroll 1
                 for (int q = 0; q < NG64; ++q) {
                     const int mt = q / GPM, c = q % GPM;
-                    if constexpr (Cfg::RA > 0) {
-                        if (q == GPM) {   // first group of sub-tile 1: its MMAs are committed separately
-                            mbar_wait(tfull1_bar(as), aph, sk, 7, tile, q);
-                            tc_fence_after();
-                        }
-                    }
                     const int row_t = m0 + (CG == 2 ? mt * 256 + static_cast<int>(rank) * 128 : mt * 128) + wq * 32;
                     uint32_t o[32];
                     {
@@ -753,7 +626,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
         const int t = (threadIdx.x - 256) % XT;
         const uint32_t seed_lo = static_cast<uint32_t>(p.seed), seed_hi = static_cast<uint32_t>(p.seed >> 32);
         const uint32_t thr = p.thresh16;
-        [[maybe_unused]] const uint32_t mask_bytes32 = static_cast<uint32_t>(p.mask_bytes);   // < 4 GB, checked by the host
         uint32_t it = 0;   // ring position over all k-blocks of all tiles
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
             int mt_i, nt_i, split;
@@ -772,7 +644,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 // after it had seen phase u-2) puts full_bar(s) at phase >= u, which makes the parity wait exact too.
                 static_assert(XG <= STAGES, "transform groups: the producer-order argument above needs XG <= STAGES");
                 mbar_wait(empty_bar(s), ph ^ 1u, sk, 16, tile, kb);
-                if constexpr (!Cfg::XF_BITS) mbar_wait(full_bar(s), ph, sk, 8, tile, kb);
+                mbar_wait(full_bar(s), ph, sk, 8, tile, kb);
                 // hash counter of chunk i = counter of chunk 0 + a multiple of xf_ld (XT = 128: rows advance by 16 per chunk)
                 uint32_t j0_base;
                 {
@@ -782,29 +654,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     j0_base = static_cast<uint32_t>(static_cast<unsigned long long>(e_base) >> 2);
                 }
                 const uint32_t j0_step = static_cast<uint32_t>(p.xf_ld) * 4u;   // 16 rows further = 16 * xf_ld elements = 4 * xf_ld counters
-                if constexpr (Cfg::XF_BITS) {
-                    // mask bytes of this thread's eight chunks (byte index = element index / 8 = counter / 2): they depend
-                    // only on the position, so the loads are in flight while the thread waits for the operand tile
-                    uint32_t mb[1024 / XT];
-#pragma unroll
-                    for (int i = 0; i < 1024 / XT; ++i) {
-                        const uint32_t j0 = Cfg::A_MN ? j0_base + static_cast<uint32_t>(i & 3) * j0_step + static_cast<uint32_t>(i >> 2) * 16u
-                                                      : j0_base + static_cast<uint32_t>(i) * j0_step;
-                        const uint32_t bi = j0 >> 1;
-                        mb[i] = bi < mask_bytes32 ? static_cast<uint32_t>(__ldg(p.mask_bits + bi)) : 0xFFu;   // past the activation: zeros anyway
-                    }
-                    mbar_wait(full_bar(s), ph, sk, 8, tile, kb);
-#pragma unroll
-                    for (int i = 0; i < 1024 / XT; ++i) {
-                        const uint32_t addr = a_stage(s) + (t + XT * i) * 16;
-                        uint32_t w[4], m[4];
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
-                        dropout_byte_to_masks(mb[i], m);
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0] & m[0]), "r"(w[1] & m[1]),
-                                     "r"(w[2] & m[2]), "r"(w[3] & m[3]) : "memory");
-                    }
-                } else
 #pragma unroll
                 for (int i = 0; i < 1024 / XT; ++i) {
                     const int q = t + XT * i;

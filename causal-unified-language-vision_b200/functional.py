@@ -296,58 +296,6 @@ def dropout_bwd_add_(dx: torch.Tensor, dxl: torch.Tensor, seed: int, p: float) -
     return dx
 
 
-# Experiment (B2Q_MASK_BITS=1, default off; not yet run on hardware): lora_down / lora_grads read a packed copy of the
-# LoRA-dropout mask (1 bit per element of x, generated once per (seed, shape) by b2q_dropout_mask_bits and kept until the
-# backward of the same module has used it) instead of hashing it in shared memory.  Same mask, same results.
-import collections  # noqa: E402
-import os  # noqa: E402
-
-_MASK_BITS = os.environ.get("B2Q_MASK_BITS", "0") == "1"
-_mask_bits_cache: "collections.OrderedDict" = collections.OrderedDict()
-_MASK_BITS_CACHE_ENTRIES = 512
-
-
-def dropout_mask_bits(shape, seed: int, p: float, device) -> torch.Tensor:
-    """Packed keep mask of a [M, K] activation: uint8 [M * K / 8], bit k of byte b = keep(seed, 8 b + k)."""
-    n = 1
-    for d in shape:
-        n *= int(d)
-    if n % 32 != 0:
-        raise ValueError("dropout_mask_bits needs a multiple of 32 elements")
-    bits = torch.empty(n // 8, dtype=torch.uint8, device=device)
-    _need_cuda(bits)
-    _lib.check(_lib.load().b2q_dropout_mask_bits(_p(bits), n, seed, p, _stream()), "b2q_dropout_mask_bits")
-    return bits
-
-
-class _use_mask_bits:
-    """Context: hand the packed mask of x (cached per seed / shape / stream) to the next lora_down / lora_grads launch."""
-
-    def __init__(self, x: torch.Tensor, seed: int, p: float, last_use: bool):
-        self.on = _MASK_BITS and p > 0.0
-        if not self.on:
-            return
-        key = (int(seed), tuple(x.shape), float(p), x.device, torch.cuda.current_stream().cuda_stream)
-        bits = _mask_bits_cache.pop(key, None)
-        if bits is None:
-            bits = dropout_mask_bits(x.shape, seed, p, x.device)
-        if not last_use:
-            _mask_bits_cache[key] = bits
-            while len(_mask_bits_cache) > _MASK_BITS_CACHE_ENTRIES:
-                _mask_bits_cache.popitem(last=False)
-        self.bits = bits
-
-    def __enter__(self):
-        if self.on:
-            _lib.load().b2q_debug_set_mask_bits(_p(self.bits), self.bits.numel())
-        return self
-
-    def __exit__(self, *exc):
-        if self.on:
-            _lib.load().b2q_debug_set_mask_bits(None, 0)
-        return False
-
-
 # --------------------------------------------------------------------------- QLoRA GEMMs ----
 def lora_down(x: torch.Tensor, lora_A: torch.Tensor, scale: float, seed: int = 0, p: float = 0.0):
     """u = drop(x) @ A^T, us = scale * u   (x [M,K], A [r,K]) -> (u [M,r], us [M,r]) bf16.
@@ -359,9 +307,8 @@ def lora_down(x: torch.Tensor, lora_A: torch.Tensor, scale: float, seed: int = 0
     r = lora_A.shape[0]
     u = torch.empty((M, r), dtype=torch.bfloat16, device=x.device)
     us = torch.empty((M, r), dtype=torch.bfloat16, device=x.device)
-    with _use_mask_bits(x, seed, p, last_use=False):
-        _lib.check(_lib.load().b2q_lora_down(_p(x), _p(lora_A), scale, seed, p, _p(u), _p(us), M, K, r, _stream()),
-                   "b2q_lora_down")
+    _lib.check(_lib.load().b2q_lora_down(_p(x), _p(lora_A), scale, seed, p, _p(u), _p(us), M, K, r, _stream()),
+               "b2q_lora_down")
     return u, us
 
 
@@ -444,9 +391,8 @@ def lora_grads(dy, x, u, du, scale: float, dA: torch.Tensor, dB: torch.Tensor, a
     lib = _lib.load()
     nbytes = int(lib.b2q_lora_grads_workspace_bytes(M, N, K, r))
     ws = _workspace(nbytes, dy.device)
-    with _use_mask_bits(x, seed, p, last_use=True):
-        _lib.check(lib.b2q_lora_grads(_p(dy), _p(x), _p(u), _p(du), scale, seed, p, _p(dA), _p(dB), int(accumulate), _p(ws),
-                                      ws.numel(), M, N, K, r, _stream()), "b2q_lora_grads")
+    _lib.check(lib.b2q_lora_grads(_p(dy), _p(x), _p(u), _p(du), scale, seed, p, _p(dA), _p(dB), int(accumulate), _p(ws),
+                                  ws.numel(), M, N, K, r, _stream()), "b2q_lora_grads")
     return dA, dB
 
 

@@ -96,9 +96,7 @@ int b2q_gemv_4bit(const void* x_bf16, const b2q_nf4_weight* w, void* y_bf16, int
  * CPU oracle regenerate the same mask from (seed, p).  Torch's Philox stream is not reproduced
  * (SURVEY.md section 7.3). */
 int b2q_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, float p, cudaStream_t stream);
-/* Packed form of the same mask: bit k of byte b = keep(seed, 8 b + k); n elements, n % 32 == 0, `bits` 16-byte aligned
- * and n / 8 bytes long.  Experiment (not yet run on hardware): see b2q_debug_set_mask_bits. */
-int b2q_dropout_mask_bits(void* bits, int64_t n, uint64_t seed, float p, cudaStream_t stream);
+
 /* xd = bf16(x * keep / (1 - p)) */
 int b2q_dropout_apply(const void* x_bf16, void* xd_bf16, int64_t n, uint64_t seed, float p, cudaStream_t stream);
 /* dx[i] += bf16(dxl[i] * keep / (1 - p))  (backward of the dropout on the LoRA branch) */
@@ -218,11 +216,6 @@ int b2q_comm_destroy(b2q_comm* comm);
  * committed, 5 epilogue sees the accumulator, 6 epilogue done.  NULL switches it off (default). */
 int b2q_debug_set_trace(void* buf, int tiles_per_cta);
 
-/* Experiment: when bits != NULL the following b2q_lora_down / b2q_lora_grads calls with drop_p > 0 read the packed mask
- * of their activation x [M,K] (b2q_dropout_mask_bits with the same seed and p, M * K / 8 bytes) instead of hashing it in
- * shared memory -- the hash is then computed once per module and step instead of three times.  NULL (default) restores
- * the in-kernel hash.  Results are identical either way. */
-int b2q_debug_set_mask_bits(const void* bits, int64_t bytes);
 
 /* Tuning: L2 prefetch distance (in 64-wide k-blocks) of the activation operand in the tcgen05 GEMMs; 0 = off. */
 int b2q_debug_set_prefetch(int kblocks);

@@ -27,7 +27,6 @@ def test_c_host_example_compiles_and_links_as_plain_c(lib_built, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("B2Q_EXPERIMENTAL") != "1", reason="not yet run on hardware (B2Q_EXPERIMENTAL=1)")
 def test_c_host_example_runs(lib_built, tmp_path):
     exe = build_example(str(tmp_path))
     env = dict(os.environ, LD_LIBRARY_PATH=PKG + ":" + os.path.join(CUDA, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))

@@ -113,8 +113,7 @@ CASES = [  # M, N, K, r, double_quant
 ]
 
 
-# variant 6 (run-ahead issue order) is an experiment that has not run on hardware yet: B2Q_EXPERIMENTAL=1 adds it
-VARIANTS = [0, 1, 2, 3, 4, 5] + ([6] if os.environ.get("B2Q_EXPERIMENTAL") == "1" else [])
+VARIANTS = [0, 1, 2, 3, 4, 5]
 
 
 @pytest.mark.parametrize("M,N,K,r,dq", CASES)
@@ -450,60 +449,6 @@ def test_dropout_mask_golden_fixture_on_gpu(F, cuda_dev):
         m = F.dropout_mask(tuple(c["shape"]), c["seed"], c["p"], cuda_dev).cpu().numpy()
         assert int(m.sum()) == c["kept"]
         assert hashlib.sha256(np.packbits(m).tobytes()).hexdigest() == c["sha256"], c
-
-
-@pytest.mark.skipif(os.environ.get("B2Q_EXPERIMENTAL") != "1", reason="experiments not yet run on hardware (B2Q_EXPERIMENTAL=1)")
-def test_experimental_variant6_bit_identical_to_default(F, cuda_dev):
-    """Variant 6 issues the same MMAs in the same order per accumulator element: outputs must equal variant 5 bit for bit."""
-    stackmod = importlib.import_module("causal-unified-language-vision_b200.stack")
-    gen = torch.Generator(device=cuda_dev).manual_seed(3)
-    lin = stackmod.make_quantized_linear(1024, 2048, cuda_dev, gen)
-    packed, qs = lin.weight.data, lin.weight.quant_state
-    x = torch.randn(1536, 2048, device=cuda_dev, dtype=torch.bfloat16)
-    dy = torch.randn(1536, 1024, device=cuda_dev, dtype=torch.bfloat16)
-    outs = {}
-    for v in (5, 6):
-        F.set_variant(v, v)
-        try:
-            outs[v] = (F.qlora_fwd(x, packed, qs, None, None), F.qlora_bwd_dx(dy, packed, qs, None, None))
-            torch.cuda.synchronize()
-        finally:
-            F.set_variant(-1, -1)
-    assert torch.equal(outs[5][0], outs[6][0]) and torch.equal(outs[5][1], outs[6][1])
-
-
-@pytest.mark.skipif(os.environ.get("B2Q_EXPERIMENTAL") != "1", reason="experiments not yet run on hardware (B2Q_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("M,K,r", [(512, 768, 64), (333, 1024, 128)])
-def test_experimental_mask_bits_path_is_bit_identical(F, cuda_dev, M, K, r):
-    """Packed-mask experiment: the bits equal the exported byte mask, and lora_down / lora_grads give the same bits
-    whether they hash the mask in shared memory or read the packed copy."""
-    seed, p, N = 4242, 0.05, 512
-    ref_mask = F.dropout_mask((M, K), seed, p, cuda_dev).cpu().numpy().reshape(-1)
-    if (M * K) % 32 == 0:
-        bits = F.dropout_mask_bits((M, K), seed, p, cuda_dev).cpu().numpy()
-        assert np.array_equal(np.unpackbits(bits, bitorder="little"), ref_mask)
-    gen = torch.Generator(device=cuda_dev).manual_seed(1)
-    x = torch.randn(M, K, device=cuda_dev, generator=gen).bfloat16()
-    dy = (torch.randn(M, N, device=cuda_dev, generator=gen) / N ** 0.5).bfloat16()
-    A = (torch.randn(r, K, device=cuda_dev, generator=gen) / K ** 0.5).bfloat16()
-    B = (torch.randn(N, r, device=cuda_dev, generator=gen) * 0.02).bfloat16()
-    outs = {}
-    for on in (False, True):
-        if on and (M * K) % 32 != 0:
-            continue
-        F._MASK_BITS = on
-        try:
-            u, us = F.lora_down(x, A, 0.25, seed, p)
-            du = F.lora_bwd_du(dy, B, 0.25)
-            dA, dB = torch.zeros_like(A), torch.zeros_like(B)
-            F.lora_grads(dy, x, u, du, 0.25, dA, dB, seed=seed, p=p)
-            torch.cuda.synchronize()
-            outs[on] = (u, us, dA, dB)
-        finally:
-            F._MASK_BITS = False
-    if True in outs:
-        for a, b in zip(outs[False], outs[True]):
-            assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("dq", [True, False])

@@ -188,10 +188,6 @@ def test_dropout_mask_restatement_matches_the_product_source_and_is_well_behaved
         out = subprocess.run([exe, str(seed), str(p), str(n)], capture_output=True, text=True, check=True).stdout.strip()
         ref = np.frombuffer(out.encode(), dtype=np.uint8) - ord("0")
         assert np.array_equal(ref, dropout.keep_mask((n,), seed, p)), (seed, p)
-    # packed-mask helpers of the product (dropout_bits32, dropout_byte_to_masks) against dropout_keep, on the host
-    for seed, p in ((1234, 0.05), (0x3FFFFFFFFFFFFFF1, 0.5)):
-        out = subprocess.run([exe, str(seed), str(p), "8192", "bits"], capture_output=True, text=True)
-        assert out.returncode == 0 and "bits ok" in out.stdout, out.stdout
     m = dropout.keep_mask((1024, 4096), 0x1234ABCD5678, 0.05).astype(np.float64)
     d = 1.0 - m
     assert abs(d.mean() - 0.05) < 5e-4
