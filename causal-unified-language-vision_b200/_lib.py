@@ -54,7 +54,7 @@ SIGNATURES = {
                               c_void_p]),
     "b2q_qlora_fwd": (c_int, [c_void_p, ct.POINTER(NF4Weight), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_int, c_void_p]),
-    "b2q_lora_bwd_du": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b2q_lora_bwd_du": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2q_qlora_bwd_dx": (c_int, [c_void_p, ct.POINTER(NF4Weight), c_void_p, c_void_p, c_u64, c_float, c_void_p, c_int,
                                  c_int, c_int, c_int, c_void_p]),
     "b2q_lora_grads_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

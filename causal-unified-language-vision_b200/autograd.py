@@ -110,7 +110,7 @@ class QLoRALinear(torch.autograd.Function):
         x2, packed, a, b, u = ctx.saved_tensors
         dy2, _ = _flatten(dy)
         need_x, need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
-        du = F.lora_bwd_du(dy2, b, ctx.scale)
+        du = F.lora_bwd_du(dy2, b, ctx.scale, ctx.p)   # keep-scale of the LoRA dropout folded in
         dx = None
         if need_x:
             dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, du, a, ctx.seed, ctx.p)

@@ -493,41 +493,20 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
     memset(&p, 0, sizeof(p));
     fill_weight(p, w, K);
     p.D = dx; p.D2 = nullptr; p.ldd = K; p.alpha = 1.f; p.alpha2 = 0.f;
-    const bool tail = lora && !masked;
-    p.M = M; p.N = K; p.kb_main = N / 64; p.kb_tail = tail ? r / 64 : 0; p.splits = 1;
+    p.M = M; p.N = K; p.kb_main = N / 64; p.kb_tail = lora ? r / 64 : 0; p.splits = 1;
     auto setup = [&](int bnc, int group_m) -> int {
         p.group_m = group_m;
         if ((e = map_bf16_kmajor(&p.tmA, dy, M, N, 128))) return e;
         // packed W [N rows][K/2 bytes]: box (bnc/2 bytes) x 64 rows
         if ((e = make_map_2d(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->packed, K / 2, N, K / 2, bnc / 2, 64, false)))
             return e;
-        if (tail) {
+        if (lora) {
             if ((e = map_bf16_kmajor(&p.tmA2, du, M, r, 128))) return e;
             if ((e = map_bf16_mnmajor(&p.tmB2, lora_A, r, K))) return e;
         }
         return 0;
     };
     auto slab = [&](int tile_m) { int g = static_cast<int>((32ll << 20) / (2ll * N * tile_m)); return g < 1 ? 1 : g; };
-    // Experiment hook (B2Q_DX_MASK_FIRST=1, variants 4/5 only, default off): write the masked LoRA term first with plain
-    // stores and let the decode GEMM's epilogue accumulate onto it with L2 reductions, instead of the other way round.
-    static const int mask_first_env = env_int("B2Q_DX_MASK_FIRST", 0);
-    const bool mask_first = masked && mask_first_env != 0 && variant >= 4;
-    auto masked_term = [&](int accumulate) -> int {
-        // LoRA dropout: dx (+)= keep * (du @ A) / (1 - p) -- masked epilogue; accumulate = reduce-add into dx at the L2
-        GemmParams q;
-        memset(&q, 0, sizeof(q));
-        q.D = dx; q.ldd = K; q.alpha = 1.0f / (1.0f - drop_p); q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
-        q.accum_d = accumulate;
-        q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.xf_ld = K;
-        int eq;
-        if ((eq = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return eq;
-        if ((eq = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return eq;
-        return launch<GemmKNMask>(q, stream);
-    };
-    if (mask_first) {
-        if ((e = masked_term(0))) return e;
-        p.accum_d = 1;
-    }
     switch (variant) {
         case 0: if ((e = setup(DxV0::BNC, slab(DxV0::TILE_M)))) return e; e = launch<DxV0>(p, stream); break;
         case 1: if ((e = setup(DxV1::BNC, slab(DxV1::TILE_M)))) return e; e = launch<DxV1>(p, stream); break;
@@ -540,8 +519,17 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
             break;
         default: if ((e = setup(DxV5::BNC, slab(DxV5::TILE_M)))) return e; e = launch<DxV5>(p, stream); break;
     }
-    if (e || !masked || mask_first) return e;
-    return masked_term(1);
+    if (e || !masked) return e;
+    // LoRA dropout: the tail k-blocks added du @ A (du carries 1 / (1 - p)) to every element; take it back out of the
+    // dropped ones: dx -= (1 - keep) * (du @ A), masked epilogue with the inverted mask, sparse reductions at the L2
+    GemmParams q;
+    memset(&q, 0, sizeof(q));
+    q.D = dx; q.ldd = K; q.alpha = -1.0f; q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
+    q.accum_d = 1;
+    q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.mask_flip = 0xFFFFFFFFu; q.xf_ld = K;
+    if ((e = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return e;
+    if ((e = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return e;
+    return launch<GemmKNMask>(q, stream);
 }
 
 template <int R>
@@ -573,7 +561,7 @@ extern "C" int b2q_lora_down(const void* x, const void* lora_A, float scale, uin
 }
 
 template <int R>
-static int lora_du_r(const void* dy, const void* lora_B, float scale, void* du, int M, int N, cudaStream_t stream) {
+static int lora_du_r(const void* dy, const void* lora_B, float scale, void* du, int M, int N, cudaStream_t stream) {   // scale: keep-scale included
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.D = du; p.D2 = nullptr; p.ldd = R; p.alpha = scale;
@@ -585,11 +573,13 @@ static int lora_du_r(const void* dy, const void* lora_B, float scale, void* du, 
     return launch<DuCfg<R>>(p, stream);
 }
 
-extern "C" int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, void* du, int M, int N, int r,
+extern "C" int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, float drop_p, void* du, int M, int N, int r,
                                cudaStream_t stream) {
     if (M == 0) return 0;
     if (dy == nullptr || lora_B == nullptr || du == nullptr) return B2Q_ERR_ARG;
     if (N % 64 != 0) return B2Q_ERR_SHAPE;
+    if (!(drop_p >= 0.f && drop_p < 1.f)) return B2Q_ERR_ARG;
+    scale = scale / (1.0f - drop_p);
     if (r == 64) return lora_du_r<64>(dy, lora_B, scale, du, M, N, stream);
     if (r == 128) return lora_du_r<128>(dy, lora_B, scale, du, M, N, stream);
     return B2Q_ERR_SHAPE;
@@ -622,8 +612,7 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
         if ((e = map_bf16_mnmajor(&p.tmB, du, M, R))) return e;
         if (drop_p > 0.f) e = launch<GradADropCfg<R>>(p, stream); else e = launch<GradACfg<R>>(p, stream);
         if (e) return e;
-        if ((e = b2q_reduce_partials(wa, sa, static_cast<int64_t>(R) * K, 1.0f / (1.0f - drop_p), dA, accumulate,
-                                     stream)))
+        if ((e = b2q_reduce_partials(wa, sa, static_cast<int64_t>(R) * K, 1.0f, dA, accumulate, stream)))   // du carries 1 / (1 - p)
             return e;
     }
     // dB[n, j] = scale * sum_m dy[m, n] * u[m, j]

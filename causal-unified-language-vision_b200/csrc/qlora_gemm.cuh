@@ -67,6 +67,7 @@ struct GemmParams {
     // activation the mask belongs to (b2q_internal.h dropout_keep)
     unsigned long long seed;
     unsigned int thresh16;
+    unsigned int mask_flip;   // EPI_BF16_MASK: 0 = keep the kept elements, 0xFFFFFFFF = keep the DROPPED ones (dX correction)
     long long xf_ld;
     // optional phase trace (debug / profiling): clock64 stamps, [cta][tile][8]; nullptr = off
     long long* trace;
@@ -459,13 +460,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         const unsigned long long e0 = static_cast<unsigned long long>(row_t + lane) * p.xf_ld + (n0 + c * 64);
                         const uint32_t j0 = static_cast<uint32_t>(e0 >> 2);
                         const uint32_t s_lo = static_cast<uint32_t>(p.seed), s_hi = static_cast<uint32_t>(p.seed >> 32);
-                        const uint32_t thr = p.thresh16;
+                        const uint32_t thr = p.thresh16, flip = p.mask_flip;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {   // one 64-bit hash per four elements (two packed words)
                             uint32_t ha, hb;
                             dropout_hash64(s_lo, s_hi, j0 + j, ha, hb);
-                            o[2 * j] &= dropout_mask2(ha, thr);
-                            o[2 * j + 1] &= dropout_mask2(hb, thr);
+                            o[2 * j] &= dropout_mask2(ha, thr) ^ flip;
+                            o[2 * j + 1] &= dropout_mask2(hb, thr) ^ flip;
                         }
                     }
                     if (c == GPM - 1) {   // sub-tile mt drained: its last TMEM load has completed
@@ -508,10 +509,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                         __nv_bfloat16* gp = Dp + static_cast<long long>(row_w) * ldd_r + (n0 + c * 64 + ch * 8);
                         if (accum_r) {
                             // D += tile: 128-bit vector reductions performed at the L2 (fire and forget, no read into
-                            // the SM); bf16 add with round-to-nearest, i.e. D = bf16(D + bf16(alpha * acc))
+                            // the SM); bf16 add with round-to-nearest, i.e. D = bf16(D + bf16(alpha * acc)).  A vector of
+                            // eight zeros changes nothing and is not sent: the dX correction keeps only the ~5 % of
+                            // elements the dropout mask dropped, so two thirds of its vectors are empty and the L2
+                            // reduction rate, which bounds this kernel, is spent on the third that is not.
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const uint32_t ok = (row_w + i * 4 < M_r) ? 1u : 0u;
+                                const uint32_t ok = (row_w + i * 4 < M_r && (val[i].x | val[i].y | val[i].z | val[i].w) != 0u) ? 1u : 0u;
                                 asm volatile("{\n\t.reg .pred P1;\n\tsetp.ne.b32 P1, %5, 0;\n\t@P1 red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};\n\t}\n"
                                              ::"l"(gp + static_cast<long long>(i) * 4 * ldd_r), "r"(val[i].x), "r"(val[i].y),
                                                "r"(val[i].z), "r"(val[i].w), "r"(ok) : "memory");
@@ -551,9 +555,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                                     uint32_t ha, hb;
                                     dropout_hash64(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32), j0 + j, ha, hb);
                                     o[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j]) * p.alpha, __uint_as_float(v[4 * j + 1]) * p.alpha) &
-                                               dropout_mask2(ha, p.thresh16);
+                                               (dropout_mask2(ha, p.thresh16) ^ p.mask_flip);
                                     o[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) * p.alpha, __uint_as_float(v[4 * j + 3]) * p.alpha) &
-                                                   dropout_mask2(hb, p.thresh16);
+                                                   (dropout_mask2(hb, p.thresh16) ^ p.mask_flip);
                                 }
                             } else if (p.accum_d) {
 #pragma unroll
@@ -753,7 +757,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     // of the slot -- a few tiles per thousand launches were off by 3-14 % of max|y| (round 2, DESIGN.md
                     // section 4; whether it happened depended on where ptxas scheduled the first consumer of w[]).  The
                     // warp-wide reduction reads all eight words of all 32 lanes, the store keeps it alive.
+#ifdef B2Q_FENCE_LIGHT
+                    // lighter form under test: one consumer of the last word of each LDS.128 (the scoreboard of a load covers
+                    // the whole warp instruction), no cross-lane reduction
+                    const uint32_t x = w[3] ^ w[7];
+                    __syncwarp();
+#else
                     const uint32_t x = __reduce_xor_sync(0xffffffffu, w[0] ^ w[1] ^ w[2] ^ w[3] ^ w[4] ^ w[5] ^ w[6] ^ w[7]);
+#endif
                     if (lane == 0) {
                         asm volatile("st.shared.u32 [%0], %1;" ::"r"(tmem_slot + 8u), "r"(x) : "memory");
                         mbar_arrive(pk_empty_bar(ps));  // packed slot may be refilled

@@ -333,21 +333,22 @@ def qlora_fwd(x: torch.Tensor, packed: torch.Tensor, qs: QuantState, us: Optiona
     return y
 
 
-def lora_bwd_du(dy: torch.Tensor, lora_B: torch.Tensor, scale: float) -> torch.Tensor:
-    """du = scale * dy @ B   (dy [M,N], B [N,r]) -> [M,r] bf16."""
+def lora_bwd_du(dy: torch.Tensor, lora_B: torch.Tensor, scale: float, p: float = 0.0) -> torch.Tensor:
+    """du = scale / (1 - p) * dy @ B   (dy [M,N], B [N,r]) -> [M,r] bf16: the gradient of the LoRA hidden activation with
+    the keep-scale of the LoRA dropout folded in (``qlora_bwd_dx`` and ``lora_grads`` both expect it that way)."""
     _need_cuda(dy, lora_B)
     _need(dy, torch.bfloat16, "dy")
     _need(lora_B, torch.bfloat16, "lora_B")
     M, N = dy.shape
     r = lora_B.shape[1]
     du = torch.empty((M, r), dtype=torch.bfloat16, device=dy.device)
-    _lib.check(_lib.load().b2q_lora_bwd_du(_p(dy), _p(lora_B), scale, _p(du), M, N, r, _stream()), "b2q_lora_bwd_du")
+    _lib.check(_lib.load().b2q_lora_bwd_du(_p(dy), _p(lora_B), scale, p, _p(du), M, N, r, _stream()), "b2q_lora_bwd_du")
     return du
 
 
 def qlora_bwd_dx(dy: torch.Tensor, packed: torch.Tensor, qs: QuantState, du: Optional[torch.Tensor],
                  lora_A: Optional[torch.Tensor], seed: int = 0, p: float = 0.0) -> torch.Tensor:
-    """dx = dy @ dequant(W) (+ keep * (du @ A) / (1-p)).  dy [M,N] bf16 -> dx [M,K] bf16."""
+    """dx = dy @ dequant(W) (+ keep * (du @ A)) with ``du = lora_bwd_du(dy, B, scale, p)``.  dy [M,N] bf16 -> dx [M,K] bf16."""
     _need_cuda(dy, packed, du, lora_A)
     _need(dy, torch.bfloat16, "dy")
     M, N = dy.shape
@@ -380,8 +381,8 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 def lora_grads(dy, x, u, du, scale: float, dA: torch.Tensor, dB: torch.Tensor, accumulate: bool = False,
                seed: int = 0, p: float = 0.0):
-    """dA[r,K] (+)= du^T @ drop(x) ; dB[N,r] (+)= scale * dy^T @ u.  dA / dB are written in place
-    (they may be views into a flat gradient bucket)."""
+    """dA[r,K] (+)= du^T @ (keep * x) ; dB[N,r] (+)= scale * dy^T @ u, with ``du = lora_bwd_du(dy, B, scale, p)`` (keep-scale
+    included).  dA / dB are written in place (they may be views into a flat gradient bucket)."""
     _need_cuda(dy, x, u, du, dA, dB)
     for t, nm in ((dy, "dy"), (x, "x"), (u, "u"), (du, "du"), (dA, "dA"), (dB, "dB")):
         _need(t, torch.bfloat16, nm)

@@ -133,7 +133,7 @@ class QLoRALinearStack(nn.Module):
                 u, us = F.lora_down(x, A, s, seed, p)
                 y = F.qlora_fwd(x, packed, qs, us, B)
                 del y, us
-            du = F.lora_bwd_du(dy, B, s)
+            du = F.lora_bwd_du(dy, B, s, p)
             dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)
             sink = self.sync.sink_for(mod)
             F.lora_grads(dy, x, u, du, s, sink.dA, sink.dB, accumulate=sink.accumulate(), seed=seed, p=p)

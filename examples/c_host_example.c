@@ -124,7 +124,7 @@ int main(void) {
     const uint64_t launches0 = b2q_launch_count();
     CK(b2q_lora_down(dx_in, dA_w, s, 0, 0.f, d_u, d_us, M, K, r, 0));
     CK(b2q_qlora_fwd(dx_in, &w, d_us, dB_w, d_y, M, N, K, r, 0));
-    CK(b2q_lora_bwd_du(d_dy, dB_w, s, d_du, M, N, r, 0));
+    CK(b2q_lora_bwd_du(d_dy, dB_w, s, 0.f, d_du, M, N, r, 0));
     CK(b2q_qlora_bwd_dx(d_dy, &w, d_du, dA_w, 0, 0.f, d_dx, M, N, K, r, 0));
     CK(b2q_lora_grads(d_dy, dx_in, d_u, d_du, s, 0, 0.f, d_gA, d_gB, 0, d_ws, ws_bytes, M, N, K, r, 0));
     CU(cudaDeviceSynchronize());

@@ -127,20 +127,26 @@ int b2q_lora_down(const void* x, const void* lora_A, float scale, uint64_t seed,
 int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void* us, const void* lora_B, void* y, int M, int N,
                   int K, int r, cudaStream_t stream);
 
-/* du = bf16(scale * dy @ lora_B).  Replaces the autograd backward of `lora_B` (+ `* scaling`). */
-int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, void* du, int M, int N, int r,
+/* du = bf16(scale / (1 - drop_p) * dy @ lora_B): the gradient of the LoRA hidden activation with the keep-scale of the
+ * LoRA dropout folded in -- both of its consumers (dx and dA below) need exactly du / (1 - drop_p), so it is applied
+ * once, in this kernel's epilogue.  drop_p = 0: plain scale * dy @ lora_B.
+ * Replaces the autograd backward of `lora_B` (+ `* scaling`) and the 1 / (1 - p) of the dropout's backward. */
+int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, float drop_p, void* du, int M, int N, int r,
                     cudaStream_t stream);
 
-/* dx = dy @ dequant(W) + keep * (du @ lora_A) / (1 - drop_p)   (same decode, W consumed as an MN-major
- * operand, no transposed or bf16 copy of W).  du may be NULL (base only).  drop_p = 0: one kernel, the
- * LoRA term runs as tail K-blocks.  drop_p > 0: the decode GEMM writes dy @ dequant(W) to dx, then a
- * masked-epilogue GEMM reduce-adds the LoRA term into dx (two launches, no extra buffer).
+/* dx = dy @ dequant(W) + keep * (du @ lora_A)   with du from b2q_lora_bwd_du (keep-scale included; same decode as the
+ * forward, W consumed as an MN-major operand, no transposed or bf16 copy of W).  du may be NULL (base only).  The LoRA
+ * term runs as tail K-blocks of the decode GEMM into the same accumulator.  drop_p > 0: that gives
+ * dy @ dequant(W) + du @ lora_A for EVERY element; a second launch then takes the LoRA term back out of the ~5 % of
+ * elements the mask dropped (masked-epilogue GEMM with the inverted mask, 128-bit vector reductions into dx at the L2,
+ * issued only for vectors that hold a dropped element).  No extra buffer.
  * Replaces `MatMul4Bit.backward` (second dequantize_4bit + cuBLAS) plus the backward of `lora_A`,
  * of the dropout and the gradient add. */
 int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A, uint64_t seed,
                      float drop_p, void* dx, int M, int N, int K, int r, cudaStream_t stream);
 
-/* dA[r,K] (+)= du^T @ drop(x) ;  dB[N,r] (+)= scale * dy^T @ u   (bf16 outputs, fp32 split-M partials
+/* dA[r,K] (+)= du^T @ (keep * x) ;  dB[N,r] (+)= scale * dy^T @ u   (du from b2q_lora_bwd_du, keep-scale included;
+ * bf16 outputs, fp32 split-M partials
  * in `workspace`, reduced in a fixed order; the dropout mask is regenerated in shared memory from
  * (seed, drop_p)).  dA / dB may point into flat gradient buckets.
  * Replaces the weight-gradient halves of the autograd backward of `lora_A` / `lora_B`. */

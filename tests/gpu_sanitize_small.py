@@ -22,7 +22,7 @@ B = (torch.randn(N, r, device=dev) * 0.02).bfloat16()
 for p in (0.0, 0.05):
     u, us = F.lora_down(x, A, 0.25, 7, p)
     y = F.qlora_fwd(x, packed, qs, us, B)
-    du = F.lora_bwd_du(dy, B, 0.25)
+    du = F.lora_bwd_du(dy, B, 0.25, p)
     dx = F.qlora_bwd_dx(dy, packed, qs, du, A, 7, p)
     dA, dB = torch.zeros_like(A), torch.zeros_like(B)
     F.lora_grads(dy, x, u, du, 0.25, dA, dB, seed=7, p=p)

@@ -20,7 +20,7 @@ B = (torch.randn(N, r, device=dev) * 0.02).bfloat16()
 dA, dB = torch.zeros_like(A), torch.zeros_like(B)
 for _ in range(3):
     u, us = F.lora_down(x, A, 0.25, 5, 0.05)
-    du = F.lora_bwd_du(dy, B, 0.25)
+    du = F.lora_bwd_du(dy, B, 0.25, 0.05)
     dx = F.qlora_bwd_dx(dy, packed, qs, du, A, 5, 0.05)
     F.lora_grads(dy, x, u, du, 0.25, dA, dB, seed=5, p=0.05)
 torch.cuda.synchronize()

@@ -410,10 +410,11 @@ def test_full_size_mlp_projections_against_cublas_with_dropout(F, cuda_dev, N, K
     # fused path
     u, us = F.lora_down(x, A, s, seed, p)
     y = F.qlora_fwd(x, packed, qs, us, B)
-    du = F.lora_bwd_du(dy, B, s)
+    du = F.lora_bwd_du(dy, B, s, p)       # keep-scale 1 / (1 - p) folded in
     dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)
     dA, dB = torch.zeros_like(A), torch.zeros_like(B)
     F.lora_grads(dy, x, u, du, s, dA, dB, seed=seed, p=p)
+    du = (du.float() * (1 - p)).bfloat16()   # back to the reference's du for the comparison below
     # stock-torch statement of the same math (fp32 where the reference accumulates in fp32)
     W = F.dequantize_4bit(packed, qs)
     mask = F.dropout_mask((M, K), seed, p, cuda_dev).to(torch.bfloat16)
@@ -470,11 +471,12 @@ def test_baseline_c1_exact_against_oracle(F, cuda_dev, dq, p):
     assert np.array_equal(W.view(torch.int16).cpu().numpy(), nf4.dequantize_nf4(case["state"]).astype(np.int16))
     u, us = F.lora_down(x, A, s, seed, p)
     y = F.qlora_fwd(x, packed, qs, us, B)
-    du = F.lora_bwd_du(dy, B, s)
+    du = F.lora_bwd_du(dy, B, s, p)       # keep-scale 1 / (1 - p) folded in
     dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)
     dA, dB = torch.zeros_like(A), torch.zeros_like(B)
     F.lora_grads(dy, x, u, du, s, dA, dB, seed=seed, p=p)
     torch.cuda.synchronize()
+    du = (du.float() * (1 - p)).bfloat16()   # the oracle's du is the unscaled one
     for name, got in (("y", y), ("u", u), ("du", du), ("dx", dx), ("dA", dA), ("dB", dB)):
         assert rel_err(got.cpu(), ref[name]) <= TOL, (name, rel_err(got.cpu(), ref[name]))
 
@@ -499,8 +501,36 @@ def test_repeated_full_size_launches_agree_with_cublas_every_time(F, cuda_dev, N
             "dx_drop": (dy @ W).float() + (du_ref @ A).float() * mask / (1 - p)}
     rel = lambda a, b: float((a.float() - b).abs().max() / b.abs().max())
     for it in range(8):
-        du = F.lora_bwd_du(dy, B, s)
+        du = F.lora_bwd_du(dy, B, s, p)
         got = {"fwd": F.qlora_fwd(x, packed, qs, None, None), "dx": F.qlora_bwd_dx(dy, packed, qs, None, None),
                "dx_drop": F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)}
         for name, ref in refs.items():
             assert rel(got[name], ref) <= TOL, (name, it, rel(got[name], ref))
+
+
+@pytest.mark.parametrize("M,N,K,r", [(1000, 512, 1024, 64), (4096, 4096, 4096, 64), (777, 1024, 768, 128)])
+def test_dropout_dx_lora_term_in_isolation(F, cuda_dev, M, N, K, r):
+    """With a zero base weight dX is the LoRA term alone, keep * (du @ A) / (1 - p) -- three orders of magnitude below the
+    base term in the other tests, where a wrong sign or a wrong mask in the dropped-element correction would hide inside
+    bf16 rounding of dX.  Kept elements must match stock torch, dropped ones must come back to (numerically) zero."""
+    s, p, seed = 16.0 / r, 0.05, 31337
+    g = torch.Generator(device=cuda_dev).manual_seed(M + N)
+    packed, qs = F.quantize_4bit(torch.zeros(N, K, device=cuda_dev), compress_statistics=False)
+    assert float(F.dequantize_4bit(packed, qs).float().abs().max()) == 0.0
+    dy = (torch.empty(M, N, device=cuda_dev).normal_(generator=g) / N ** 0.5).bfloat16()
+    A = ((torch.rand(r, K, device=cuda_dev, generator=g) * 2 - 1) / K ** 0.5).bfloat16()
+    B = torch.empty(N, r, device=cuda_dev).normal_(0, 0.02, generator=g).bfloat16()
+    du = F.lora_bwd_du(dy, B, s, p)
+    du_ref = ((dy.float() @ B.float()) * (s / (1 - p)))
+    assert float((du.float() - du_ref).abs().max() / du_ref.abs().max()) <= 1e-2
+    dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p).float()
+    keep = F.dropout_mask((M, K), seed, p, cuda_dev).bool()
+    term = du.float() @ A.float()
+    scale = float(term.abs().max())
+    assert float((dx - term)[keep].abs().max()) <= 1e-2 * scale            # kept: the LoRA term, one bf16 rounding
+    assert float(dx[~keep].abs().max()) <= 2.0 ** -7 * scale               # dropped: term - term, at most an ulp apart
+    assert 0.03 < float((~keep).float().mean()) < 0.07
+    # and without dropout the tail k-block alone gives the full term
+    dx0 = F.qlora_bwd_dx(dy, packed, qs, F.lora_bwd_du(dy, B, s), A).float()
+    t0 = F.lora_bwd_du(dy, B, s).float() @ A.float()
+    assert float((dx0 - t0).abs().max()) <= 1e-2 * float(t0.abs().max())
