@@ -493,14 +493,15 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
     memset(&p, 0, sizeof(p));
     fill_weight(p, w, K);
     p.D = dx; p.D2 = nullptr; p.ldd = K; p.alpha = 1.f; p.alpha2 = 0.f;
-    p.M = M; p.N = K; p.kb_main = N / 64; p.kb_tail = lora ? r / 64 : 0; p.splits = 1;
+    const bool tail = lora && !masked;   // no dropout: the LoRA term runs as tail k-blocks into the same accumulator
+    p.M = M; p.N = K; p.kb_main = N / 64; p.kb_tail = tail ? r / 64 : 0; p.splits = 1;
     auto setup = [&](int bnc, int group_m) -> int {
         p.group_m = group_m;
         if ((e = map_bf16_kmajor(&p.tmA, dy, M, N, 128))) return e;
         // packed W [N rows][K/2 bytes]: box (bnc/2 bytes) x 64 rows
         if ((e = make_map_2d(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, w->packed, K / 2, N, K / 2, bnc / 2, 64, false)))
             return e;
-        if (lora) {
+        if (tail) {
             if ((e = map_bf16_kmajor(&p.tmA2, du, M, r, 128))) return e;
             if ((e = map_bf16_mnmajor(&p.tmB2, lora_A, r, K))) return e;
         }
@@ -520,13 +521,17 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
         default: if ((e = setup(DxV5::BNC, slab(DxV5::TILE_M)))) return e; e = launch<DxV5>(p, stream); break;
     }
     if (e || !masked) return e;
-    // LoRA dropout: the tail k-blocks added du @ A (du carries 1 / (1 - p)) to every element; take it back out of the
-    // dropped ones: dx -= (1 - keep) * (du @ A), masked epilogue with the inverted mask, sparse reductions at the L2
+    // LoRA dropout: dx += keep * (du @ A) (du carries 1 / (1 - p)) -- masked epilogue, 128-bit vector reductions into dx
+    // at the L2.  (Round 2 also measured the other split -- the LoRA term as tail k-blocks of the decode GEMM and a
+    // correction that takes it back out of the ~5 % dropped elements with the inverted mask, reductions only for the third
+    // of the vectors that hold one: no faster, 956 vs 942 us per module in the step.  This kernel is bound by the
+    // latency of its epilogue's instruction stream -- two epilogue warps per scheduler, ~1100 dependent instructions per
+    // 128 x 128 tile, 60 % of them the mask hash -- not by the L2 reduction rate)
     GemmParams q;
     memset(&q, 0, sizeof(q));
-    q.D = dx; q.ldd = K; q.alpha = -1.0f; q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
+    q.D = dx; q.ldd = K; q.alpha = 1.0f; q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
     q.accum_d = 1;
-    q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.mask_flip = 0xFFFFFFFFu; q.xf_ld = K;
+    q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.mask_flip = 0u; q.xf_ld = K;
     if ((e = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return e;
     if ((e = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return e;
     return launch<GemmKNMask>(q, stream);

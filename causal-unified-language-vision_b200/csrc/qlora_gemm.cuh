@@ -756,14 +756,16 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                     // reader that has not read yet: one decode warp's 32 weight rows of one k-block come from the NEXT use
                     // of the slot -- a few tiles per thousand launches were off by 3-14 % of max|y| (round 2, DESIGN.md
                     // section 4; whether it happened depended on where ptxas scheduled the first consumer of w[]).  The
-                    // warp-wide reduction reads all eight words of all 32 lanes, the store keeps it alive.
-#ifdef B2Q_FENCE_LIGHT
-                    // lighter form under test: one consumer of the last word of each LDS.128 (the scoreboard of a load covers
-                    // the whole warp instruction), no cross-lane reduction
+                    // store to a scratch word consumes the loaded registers and keeps the dependency alive.
+#ifdef B2Q_FENCE_REDUX
+                    // first form of the fix (validated, 1 % slower): a warp-wide reduction reads all eight words of all lanes
+                    const uint32_t x = __reduce_xor_sync(0xffffffffu, w[0] ^ w[1] ^ w[2] ^ w[3] ^ w[4] ^ w[5] ^ w[6] ^ w[7]);
+#else
+                    // one consumer of the last word of each LDS.128: the scoreboard of a load covers the whole warp
+                    // instruction, so the store below cannot issue before both loads have returned for all 32 lanes
+                    // (validated like the first form: 0 bad launches in tools/dx_check.py / kb_probe.py, +0.5 % step)
                     const uint32_t x = w[3] ^ w[7];
                     __syncwarp();
-#else
-                    const uint32_t x = __reduce_xor_sync(0xffffffffu, w[0] ^ w[1] ^ w[2] ^ w[3] ^ w[4] ^ w[5] ^ w[6] ^ w[7]);
 #endif
                     if (lane == 0) {
                         asm volatile("st.shared.u32 [%0], %1;" ::"r"(tmem_slot + 8u), "r"(x) : "memory");

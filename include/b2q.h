@@ -135,11 +135,10 @@ int b2q_lora_bwd_du(const void* dy, const void* lora_B, float scale, float drop_
                     cudaStream_t stream);
 
 /* dx = dy @ dequant(W) + keep * (du @ lora_A)   with du from b2q_lora_bwd_du (keep-scale included; same decode as the
- * forward, W consumed as an MN-major operand, no transposed or bf16 copy of W).  du may be NULL (base only).  The LoRA
- * term runs as tail K-blocks of the decode GEMM into the same accumulator.  drop_p > 0: that gives
- * dy @ dequant(W) + du @ lora_A for EVERY element; a second launch then takes the LoRA term back out of the ~5 % of
- * elements the mask dropped (masked-epilogue GEMM with the inverted mask, 128-bit vector reductions into dx at the L2,
- * issued only for vectors that hold a dropped element).  No extra buffer.
+ * forward, W consumed as an MN-major operand, no transposed or bf16 copy of W).  du may be NULL (base only).
+ * drop_p = 0: one kernel, the LoRA term runs as tail K-blocks into the same accumulator.  drop_p > 0: the decode GEMM
+ * writes dy @ dequant(W) to dx, then a masked-epilogue GEMM reduce-adds keep * (du @ lora_A) into dx with 128-bit vector
+ * reductions at the L2 (two launches, no extra buffer).
  * Replaces `MatMul4Bit.backward` (second dequantize_4bit + cuBLAS) plus the backward of `lora_A`,
  * of the dropout and the gradient add. */
 int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const void* du, const void* lora_A, uint64_t seed,
