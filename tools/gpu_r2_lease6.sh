@@ -22,4 +22,4 @@ for which in fwd dx; do
 done
 K="python tests/gpu_skinny_once.py"
 timeout 200 $K > $O/skinny.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none -k regex:qlora_gemm --launch-skip 14 --launch-count 7 -f -o $O/full_skinny $K > $O/ncu_full_skinny.log 2>&1; S "ncu full skinny rc=$?"
+timeout 900 ncu --set full --clock-control none -k regex:qlora_gemm --launch-skip 12 --launch-count 6 -f -o $O/full_skinny $K > $O/ncu_full_skinny.log 2>&1; S "ncu full skinny rc=$?"
