@@ -422,9 +422,22 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     }
 }
 
+// SM count of the calling thread's current device (cached per device)
+static int sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = n > 0 ? n : 148;
+    }
+    return cache[dev];
+}
+
 static int grid_for(long long work_items, int threads) {
     long long blocks = (work_items + threads - 1) / threads;
-    const long long cap = 148LL * 8;  // 8 resident 256-thread CTAs per SM, 148 SMs
+    const long long cap = static_cast<long long>(sm_count()) * 8;  // 8 resident 256-thread CTAs per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return static_cast<int>(blocks);

@@ -212,6 +212,28 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
     if (tiles == 0) return 0;
     int pairs = num_sms() / Cfg::CG;
+    if constexpr (Cfg::CG > 1) {
+        // A persistent grid larger than what can be co-resident only serialises its tail: ask the runtime how many
+        // clusters of this configuration fit (GPCs with an odd SM count cannot host a pair on their last SM).
+        static std::atomic<int> max_clusters[64];
+        const int di = dev & 63;
+        int mc = max_clusters[di].load(std::memory_order_relaxed);
+        if (mc == 0) {
+            cudaLaunchConfig_t qc{};
+            qc.gridDim = dim3(pairs * Cfg::CG);
+            qc.blockDim = dim3(Cfg::THREADS);
+            qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = Cfg::CG; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, qlora_gemm_kernel<Cfg>, &qc) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = pairs; }
+            mc = n;
+            max_clusters[di].store(mc, std::memory_order_relaxed);
+        }
+        if (pairs > mc) pairs = mc;
+    }
     if (tiles < pairs) pairs = static_cast<int>(tiles);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pairs * Cfg::CG);
@@ -350,7 +372,7 @@ extern "C" int b2q_debug_stall_report(char* out, size_t cap) {
                  "M %u N %u kb_main %u kb_tail %u splits %u tiles %u\n",
                  i, c, c & 3u, (c >> 2) & 3u, ((c >> 4) & 15u) * 64u, (c >> 8) & 1u, (c >> 9) & 1u, (c >> 10) & 1u,
                  (c >> 11) & 3u, (c >> 13) & 15u, (c >> 17) & 1u, ((c >> 18) & 1u) ? "coal" : ((c >> 19) & 1u) ? "tma" : "row",
-                 ((c >> 20) & 1u) + 1u, r[2], r[13], r[9], r[11], r[3], r[3] >> 5, r[4], stall_site_name(r[4]),
+                 ((c >> 20) & 3u) + 1u, r[2], r[13], r[9], r[11], r[3], r[3] >> 5, r[4], stall_site_name(r[4]),
                  r[5], r[6], static_cast<int>(r[7]), static_cast<int>(r[8]), r[14], r[15], r[16], r[17], r[18], r[19]);
         t += line;
         const uint32_t nb = r[10] < static_cast<uint32_t>(STALL_MAX_BARS) ? r[10] : static_cast<uint32_t>(STALL_MAX_BARS);
@@ -522,16 +544,21 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
     }
     if (e || !masked) return e;
     // LoRA dropout: dx += keep * (du @ A) (du carries 1 / (1 - p)) -- masked epilogue, 128-bit vector reductions into dx
-    // at the L2.  (Round 2 also measured the other split -- the LoRA term as tail k-blocks of the decode GEMM and a
-    // correction that takes it back out of the ~5 % dropped elements with the inverted mask, reductions only for the third
-    // of the vectors that hold one: no faster, 956 vs 942 us per module in the step.  This kernel is bound by the
-    // latency of its epilogue's instruction stream -- two epilogue warps per scheduler, ~1100 dependent instructions per
-    // 128 x 128 tile, 60 % of them the mask hash -- not by the L2 reduction rate)
+    // at the L2.  The kernel is bound by the HBM round trip of that read-modify-write (ncu: 137 MB read + 76 MB written
+    // for a 134 MB dx, 59 us alone): most of dx has left the L2 by the time the decode GEMM ends, so every reduction pulls
+    // its line back in.  Round 2 measured three ways around it, same box, none faster: the LoRA term as tail k-blocks of
+    // the decode GEMM + a correction with the inverted mask that only touches vectors holding a dropped element (every
+    // 128-byte line still holds one), three epilogue warp sets instead of two, and hashing the mask while the TMEM loads
+    // fly.
     GemmParams q;
     memset(&q, 0, sizeof(q));
     q.D = dx; q.ldd = K; q.alpha = 1.0f; q.M = M; q.N = K; q.kb_main = r / 64; q.splits = 1;
     q.accum_d = 1;
     q.seed = seed; q.thresh16 = dropout_threshold(drop_p); q.mask_flip = 0u; q.xf_ld = K;
+    // last in, first out: same L2 slabs as the decode GEMM that has just written dx (its 512-row m-tiles are four of this
+    // kernel's), walked backwards, so that the reductions start on the slabs that are still resident
+    static const int lifo = env_int("B2Q_DX_LIFO", 1);
+    if (lifo) { q.group_m = 4 * slab(DxV5::TILE_M); q.reverse = 1; }
     if ((e = map_bf16_kmajor(&q.tmA, du, M, r, 128))) return e;
     if ((e = map_bf16_mnmajor(&q.tmB, lora_A, r, K))) return e;
     return launch<GemmKNMask>(q, stream);

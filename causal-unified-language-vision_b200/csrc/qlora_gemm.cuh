@@ -60,6 +60,8 @@ struct GemmParams {
     int kpr;           // absmax blocks per W row (= K_w / 64)          (B_DEC)
     int m_tiles, n_tiles;
     int group_m;       // rasterisation: m-tiles per L2 slab
+    int reverse;       // walk the tiles in reverse order (a kernel that revisits the previous kernel's output starts with
+                       // the part that is still in the L2)
     int tile_m;        // row stride between m-tiles, <= TILE_M (load-balancing of the skinny kernels: a tile still
                        // loads and multiplies TILE_M rows, but only stores its first tile_m -- the rest belong to the next tile)
     int accum_d;       // EPI_BF16: D = bf16(D + alpha * acc)  (read-modify-write of the caller's buffer)
@@ -85,9 +87,11 @@ struct GemmCfg {
                                    (static_cast<uint32_t>(BN_ / 64) << 4) | (A_MN_ ? 1u << 8 : 0u) | (B_MN_ ? 1u << 9 : 0u) |
                                    (B_DEC_ ? 1u << 10 : 0u) | (static_cast<uint32_t>(EPI_) << 11) |
                                    (static_cast<uint32_t>(STAGES_) << 13) | (A_XF_ ? 1u << 17 : 0u) |
-                                   (STG_ < 0 ? 1u << 18 : 0u) | (STG_ > 0 ? 1u << 19 : 0u) | (ESETS_ == 2 ? 1u << 20 : 0u);
-    // ESETS = 2: two sets of four epilogue warps (4-7 and 8-11), one per accumulator stage, for kernels that are all
-    // epilogue (one k-block per tile): set e drains the tiles whose sequence number is e (mod 2).
+                                   (STG_ < 0 ? 1u << 18 : 0u) | (STG_ > 0 ? 1u << 19 : 0u) | (static_cast<uint32_t>(ESETS_ - 1) << 20);
+    // ESETS = 2 or 3: that many sets of four epilogue warps (4-7, 8-11, 12-15), one per accumulator stage, for kernels that
+    // are all epilogue (one k-block per tile): set e drains the tiles whose sequence number is e (mod ESETS).  (Round 2
+    // measured 2 against 3 sets and the mask hash before / after the TMEM-load wait on the masked dX GEMM, same box: all
+    // four within 0.3 % -- that kernel is bound by the HBM round trip of its read-modify-write of dX, not by its epilogue.)
     static constexpr int ESETS = ESETS_;
     // STG > 0: the bf16 epilogue goes TMEM -> registers -> swizzled shared-memory staging (32 rows x 64
     // columns per epilogue warp) -> TMA store (or TMA reduce-add when accum_d), so global memory sees whole
@@ -121,7 +125,7 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES + PST * P_BYTES;
     static constexpr int ACC_COLS = MT * BN;
-    static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int ACC_STAGES = ESETS_ > 1 ? ESETS_ : ((2 * ACC_COLS <= 512) ? 2 : 1);
     static constexpr int TMEM_COLS_RAW = ACC_COLS * ACC_STAGES;
     static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
                                      : TMEM_COLS_RAW <= 256 ? 256 : 512;
@@ -137,7 +141,7 @@ struct GemmCfg {
     static constexpr int W_ALLOC = B_DEC ? 13 : 2;
     static constexpr int W_PACK = B_DEC ? 13 : -1;
     static constexpr int THREADS = 256 + NG * NDT + XF_THREADS + (ESETS_ - 1) * 128;
-    static_assert(ESETS_ == 1 || (ESETS_ == 2 && !B_DEC_ && !A_XF_ && 2 * MT_ * BN_ <= 512), "two epilogue sets: double-buffered accumulator, no decode / transform warps");
+    static_assert(ESETS_ == 1 || ((ESETS_ == 2 || ESETS_ == 3) && !B_DEC_ && !A_XF_ && ESETS_ * MT_ * BN_ <= 512), "epilogue sets: one accumulator stage each, no decode / transform warps");
     static_assert(!B_DEC || NG * NDT == 256, "decode role map assumes 8 decode warps");
     static_assert(!(A_XF_ && B_DEC_), "A transform and B decode share the warps 8+");
     static_assert(!A_XF_ || (MT_ == 1 && CG_ == 1), "A transform: single 128-row tile, single CTA");
@@ -157,6 +161,7 @@ struct GemmCfg {
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& mt, int& nt, int& split) {
     // split fastest, then m inside an L2 slab of group_m m-tiles, then n, then slab.
+    if (p.reverse) tile = p.m_tiles * p.n_tiles * p.splits - 1 - tile;
     split = tile % p.splits;
     int t = tile / p.splits;
     const int per_slab = p.group_m * p.n_tiles;
@@ -403,12 +408,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
     } else if (warp >= 4 && warp < 4 + 4 * Cfg::ESETS) {
         // ========================================================= epilogue ====
         const int wq = warp & 3;  // TMEM lane quadrant this warp may access
-        const int eset = (warp - 4) >> 2;   // epilogue set (0 unless ESETS == 2)
-        int as = Cfg::ESETS == 2 ? eset : 0;
+        const int eset = (warp - 4) >> 2;   // epilogue set (0 unless ESETS > 1)
+        int as = Cfg::ESETS > 1 ? eset : 0;
         uint32_t aph = 0;
         [[maybe_unused]] const uint32_t stg_base = smem_base + Cfg::RING_BYTES + Cfg::BAR_BYTES + Cfg::CODE256_BYTES;
-        int tseq = Cfg::ESETS == 2 ? eset : 0;
-        for (int tile = pair_id + (Cfg::ESETS == 2 ? eset * num_pairs : 0); tile < num_tiles; tile += Cfg::ESETS * num_pairs, tseq += Cfg::ESETS) {
+        int tseq = Cfg::ESETS > 1 ? eset : 0;
+        for (int tile = pair_id + (Cfg::ESETS > 1 ? eset * num_pairs : 0); tile < num_tiles; tile += Cfg::ESETS * num_pairs, tseq += Cfg::ESETS) {
             int mt_i, nt_i, split;
             tile_coords(p, tile, mt_i, nt_i, split);
             const int m0 = mt_i * p.tile_m;
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                 }
             }
             if (tr != nullptr) tr[6] = clock64();
-            if constexpr (Cfg::ESETS == 2) { aph ^= 1u; } else { if (++as == ACC_STAGES) { as = 0; aph ^= 1u; } }
+            if constexpr (Cfg::ESETS > 1) { aph ^= 1u; } else { if (++as == ACC_STAGES) { as = 0; aph ^= 1u; } }
         }
         if constexpr (Cfg::EPI_TMA) {
             if (lane == 0) tma_store_wait<0>();   // all bulk stores of this warp are complete before the CTA exits

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as ct
 import functools
+import threading
 from typing import Optional
 
 import torch
@@ -368,15 +369,20 @@ def qlora_bwd_dx(dy: torch.Tensor, packed: torch.Tensor, qs: QuantState, du: Opt
 
 
 _ws_cache: dict = {}
+_ws_lock = threading.Lock()   # backward runs on autograd engine threads, one per device
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Split-M partials of ``lora_grads``: one buffer per (device, stream), grown on demand.  Work on one stream is
+    ordered, so consecutive modules can share it; the caching allocator keeps a replaced buffer alive until the
+    kernels already enqueued on that stream are done with it."""
     key = (device, torch.cuda.current_stream().cuda_stream)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
-    return ws
+    with _ws_lock:
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            _ws_cache[key] = ws
+        return ws
 
 
 def lora_grads(dy, x, u, du, scale: float, dA: torch.Tensor, dB: torch.Tensor, accumulate: bool = False,

@@ -239,3 +239,45 @@ def test_quantise_properties_over_random_scales():
         assert np.array_equal(np.abs(peak), stq["absmax"])
 
     check()
+
+
+def test_absmax_mean_summation_order_does_not_move_the_decoded_weight():
+    """bitsandbytes takes the double-quant offset with torch's CUDA `absmax.mean()` (fp32 partial sums in a device-dependent
+    order); the oracle and the product return the correctly rounded mean.  Whatever the order, the offset moves by a few
+    ulp at most, the 8-bit absmax codes change for at most 0.2 % of the blocks (19 of 16384 for a strictly sequential
+    fp32 sum, the worst order tried; a handful for tree orders like torch's), and the decoded weight -- which uses the STORED
+    offset -- stays within one step of the 8-bit absmax code of the value either way (oracle/nf4.py
+    double_quantize_absmax).  So: decode parity with bitsandbytes does not depend on the order; quantiser BYTES may differ
+    from bitsandbytes' own in a fraction of a percent of the absmax codes."""
+    from oracle import nf4
+
+    rng = np.random.default_rng(5)
+    W = (rng.standard_normal((512, 2048)) * 0.02).astype(np.float32)
+    st = nf4.quantize_nf4(W, 64, True)
+    absmax = np.abs(W.reshape(-1, 64)).max(axis=1).astype(np.float32)
+    means = {"fp64": np.float32(absmax.astype(np.float64).mean())}
+    acc = np.float32(0.0)
+    for v in absmax:                                   # fp32, sequential
+        acc = np.float32(acc + v)
+    means["fp32 sequential"] = np.float32(acc / np.float32(absmax.size))
+    means["fp32 pairwise"] = np.float32(absmax.sum(dtype=np.float32) / np.float32(absmax.size))   # numpy's pairwise tree
+    chunks = absmax.reshape(-1, 32).sum(axis=1, dtype=np.float32)                                   # warp-sized partials
+    means["fp32 two-level"] = np.float32(chunks.sum(dtype=np.float32) / np.float32(absmax.size))
+    assert st["offset"] == means["fp64"]
+    ref = nf4.dequantize_nf4(st, as_bits=False)
+    ulp = np.spacing(np.float32(means["fp64"]))
+    for name, off in means.items():
+        assert abs(float(off) - float(means["fp64"])) <= 64 * float(ulp), name
+        # re-run the second-level quantisation with this offset
+        centred = (absmax - off).astype(np.float32)
+        blk2 = centred.reshape(-1, 256)
+        a2 = np.abs(blk2).max(axis=1).astype(np.float32)
+        q = nf4._nearest_code(st["code256"], (blk2 * (np.float32(1.0) / a2)[:, None]).astype(np.float32)).reshape(-1)
+        changed = int((q != st["absmax_q"]).sum())
+        assert changed <= absmax.size // 500, (name, changed)
+        if "sequential" not in name:
+            assert changed <= 8, (name, changed)
+        st2 = dict(st, offset=off, absmax_q=q, absmax2=a2)
+        got = nf4.dequantize_nf4(st2, as_bits=False)
+        # decoded weights agree to within one quantisation step of the 8-bit absmax code (relative 1/127 of the local scale)
+        assert float(np.abs(got - ref).max()) <= float(np.abs(ref).max()) * 2e-2, name
