@@ -111,23 +111,32 @@ class QLoRALinear(torch.autograd.Function):
         dy2, _ = _flatten(dy)
         need_x, need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         du = F.lora_bwd_du(dy2, b, ctx.scale, ctx.p)   # keep-scale of the LoRA dropout folded in
-        dx = None
-        if need_x:
-            dx = F.qlora_bwd_dx(dy2, packed, ctx.qs, du, a, ctx.seed, ctx.p)
-            dx = dx.reshape(*ctx.lead, -1).to(ctx.in_dtype)
-        dA = dB = None
-        if need_a or need_b:
+
+        def input_grad():
+            if not need_x:
+                return None
+            return F.qlora_bwd_dx(dy2, packed, ctx.qs, du, a, ctx.seed, ctx.p).reshape(*ctx.lead, -1).to(ctx.in_dtype)
+
+        def weight_grads():
+            if not (need_a or need_b):
+                return None, None
             if ctx.grad_sink is not None:
                 sink = ctx.grad_sink
                 F.lora_grads(dy2, x2, u, du, ctx.scale, sink.dA, sink.dB, accumulate=sink.accumulate(),
                              seed=ctx.seed, p=ctx.p)
                 sink.ready()  # may launch the bucket's all-reduce on the comm stream
-            else:
-                dA = torch.empty_like(a)
-                dB = torch.empty_like(b)
-                F.lora_grads(dy2, x2, u, du, ctx.scale, dA, dB, accumulate=False, seed=ctx.seed, p=ctx.p)
-                dA = dA.to(ctx.param_dtypes[0]) if need_a else None
-                dB = dB.to(ctx.param_dtypes[1]) if need_b else None
+                return None, None
+            gA = torch.empty_like(a)
+            gB = torch.empty_like(b)
+            F.lora_grads(dy2, x2, u, du, ctx.scale, gA, gB, accumulate=False, seed=ctx.seed, p=ctx.p)
+            return (gA.to(ctx.param_dtypes[0]) if need_a else None), (gB.to(ctx.param_dtypes[1]) if need_b else None)
+
+        if F.GRADS_BEFORE_DX:   # dB re-reads dy while lora_bwd_du's pass over it is still in the L2 (functional.py)
+            dA, dB = weight_grads()
+            dx = input_grad()
+        else:
+            dx = input_grad()
+            dA, dB = weight_grads()
         return dx, None, None, dA, dB, None, None, None, None
 
 

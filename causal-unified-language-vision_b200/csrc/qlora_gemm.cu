@@ -630,9 +630,25 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
                         cudaStream_t stream) {
     const int kblocks = (M + 63) / 64;
     int e;
-    // dA^T[k, j] = sum_m xd[m, k] * du[m, j]   (A = xd^T MN-major, B = du MN-major), stored transposed -> [r][K]
+    // Order: dB first.  It reads dy, which b2q_lora_bwd_du -- the call that produced `du` -- has just streamed through the L2
+    // (when the caller runs this right after it, most of a 134 MB dy is still resident); dA reads x, which nothing nearby has touched.
+    // dB[n, j] = scale * sum_m dy[m, n] * u[m, j]
     const GradPlan pa = grad_plan(K, kblocks);
     const int sa = pa.splits;
+    const GradPlan pb = grad_plan(N, kblocks);
+    const int sb = pb.splits;
+    float* wb = ws + static_cast<size_t>(sa) * R * K;
+    {
+        GemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.D = wb; p.M = N; p.N = R; p.splits = sb; p.kb_main = (kblocks + sb - 1) / sb; p.kb_tail = 0;
+        p.tile_m = pb.tile;
+        if ((e = map_bf16_mnmajor(&p.tmA, dy, M, N))) return e;
+        if ((e = map_bf16_mnmajor(&p.tmB, u, M, R))) return e;
+        if ((e = launch<GradBCfg<R>>(p, stream))) return e;
+        if ((e = b2q_reduce_partials(wb, sb, static_cast<int64_t>(N) * R, scale, dB, accumulate, stream))) return e;
+    }
+    // dA^T[k, j] = sum_m xd[m, k] * du[m, j]   (A = xd^T MN-major, B = du MN-major), stored transposed -> [r][K]
     float* wa = ws;
     {
         GemmParams p;
@@ -646,20 +662,6 @@ static int lora_grads_r(const void* dy, const void* xd, const void* u, const voi
         if (e) return e;
         if ((e = b2q_reduce_partials(wa, sa, static_cast<int64_t>(R) * K, 1.0f, dA, accumulate, stream)))   // du carries 1 / (1 - p)
             return e;
-    }
-    // dB[n, j] = scale * sum_m dy[m, n] * u[m, j]
-    const GradPlan pb = grad_plan(N, kblocks);
-    const int sb = pb.splits;
-    float* wb = ws + static_cast<size_t>(sa) * R * K;
-    {
-        GemmParams p;
-        memset(&p, 0, sizeof(p));
-        p.D = wb; p.M = N; p.N = R; p.splits = sb; p.kb_main = (kblocks + sb - 1) / sb; p.kb_tail = 0;
-        p.tile_m = pb.tile;
-        if ((e = map_bf16_mnmajor(&p.tmA, dy, M, N))) return e;
-        if ((e = map_bf16_mnmajor(&p.tmB, u, M, R))) return e;
-        if ((e = launch<GradBCfg<R>>(p, stream))) return e;
-        if ((e = b2q_reduce_partials(wb, sb, static_cast<int64_t>(N) * R, scale, dB, accumulate, stream))) return e;
     }
     return 0;
 }

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as ct
 import functools
+import os
 import threading
 from typing import Optional
 
@@ -367,6 +368,11 @@ def qlora_bwd_dx(dy: torch.Tensor, packed: torch.Tensor, qs: QuantState, du: Opt
                                             _stream()), "b2q_qlora_bwd_dx")
     return dx
 
+
+# Order of the three backward calls of one module.  lora_bwd_du streams dy through the L2; the dB GEMM inside lora_grads reads
+# dy again, so running lora_grads BEFORE qlora_bwd_dx lets it hit the part of dy that is still resident (a 134 MB dy against
+# 126 MB of L2) instead of re-reading it from HBM after the decode GEMM has flushed it.  B2Q_GRADS_BEFORE_DX=0: dx first.
+GRADS_BEFORE_DX = os.environ.get("B2Q_GRADS_BEFORE_DX", "1") == "1"
 
 _ws_cache: dict = {}
 _ws_lock = threading.Lock()   # backward runs on autograd engine threads, one per device

@@ -134,10 +134,15 @@ class QLoRALinearStack(nn.Module):
                 y = F.qlora_fwd(x, packed, qs, us, B)
                 del y, us
             du = F.lora_bwd_du(dy, B, s, p)
-            dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)
             sink = self.sync.sink_for(mod)
-            F.lora_grads(dy, x, u, du, s, sink.dA, sink.dB, accumulate=sink.accumulate(), seed=seed, p=p)
-            sink.ready()
+            if F.GRADS_BEFORE_DX:   # dB re-reads dy while lora_bwd_du's pass over it is still in the L2 (functional.py)
+                F.lora_grads(dy, x, u, du, s, sink.dA, sink.dB, accumulate=sink.accumulate(), seed=seed, p=p)
+                sink.ready()
+                dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)
+            else:
+                dx = F.qlora_bwd_dx(dy, packed, qs, du, A, seed, p)
+                F.lora_grads(dy, x, u, du, s, sink.dA, sink.dB, accumulate=sink.accumulate(), seed=seed, p=p)
+                sink.ready()
             del dx, du
         self.sync.finish()
         self._step += 1
