@@ -78,7 +78,6 @@ SIGNATURES = {
     "b2q_debug_stall_count": (c_int, []),
     "b2q_debug_stall_report": (c_int, [ct.c_char_p, c_size_t]),
     "b2q_debug_stall_selftest": (c_int, [c_void_p]),
-    "b2q_debug_mbar_probe": (c_int, [c_void_p, c_void_p]),
     "b2q_launch_count": (c_u64, []),
 }
 
