@@ -10,6 +10,7 @@ phases' bookkeeping, the watchdog wiring, and the JSON line (keys, types).  Usag
     python tests/dev_bench_dryrun.py --hang raise                 # the step dies with a CUDA-like error: same line, rc 5
 """
 import argparse
+import contextlib
 import importlib
 import json
 import os
@@ -68,6 +69,9 @@ torch.cuda.set_device = lambda d: None
 torch.cuda.synchronize = lambda *a: None
 torch.cuda.Event = FakeEvent
 torch.cuda.current_stream = lambda *a: FakeStream()
+torch.cuda.Stream = lambda *a, **k: FakeStream()
+torch.cuda.stream = lambda s: contextlib.nullcontext()
+torch.Tensor.record_stream = lambda self, s: None
 torch.device = fake_device
 torch.Tensor.pin_memory = lambda self, *a, **k: self
 

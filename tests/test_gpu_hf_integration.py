@@ -165,3 +165,49 @@ def test_hf_llama_training_loop_with_gradsync_and_fused_adamw(lib_built, cuda_de
             with torch.no_grad():
                 tp.copy_(p.detach().float())
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+def test_non_lora_trainables_are_clipped_and_stepped_with_the_lora_buckets(lib_built, cuda_dev):
+    """The reference trains `multi_modal_projector` next to the LoRA weights and clips the global norm over ALL trainable
+    parameters (/root/reference/cullavo/load_cullavo.py:128-130, pipeline/CuLLaVOPipeline.py:90-91).  Here a projector in
+    front of the decoder plays that role: registered as GradSync(extra_params=...), its gradient must enter the clip norm,
+    be scaled by the same coefficient, and be stepped by FusedLoraAdamW's companion AdamW like a stock optimizer would."""
+    par = importlib.import_module("causal-unified-language-vision_b200.parallel")
+    optim = importlib.import_module("causal-unified-language-vision_b200.optim")
+    model, lora = _build(cuda_dev)
+    torch.manual_seed(11)
+    proj = nn.Linear(32, 256, bias=True).to(cuda_dev).to(torch.bfloat16)       # "multi_modal_projector": bf16 after the sweep
+    mods = [m for m in model.modules() if isinstance(m, lora.LoraLinear4bit)]
+    sync = par.GradSync(mods, "step1", extra_params=list(proj.parameters()))
+    opt = optim.FusedLoraAdamW(sync, lr=1e-3, weight_decay=0.0, state_dtype=torch.float32)
+    assert opt.extra_optimizer is not None and len(opt.extra_params) == 2
+    twin_proj = copy.deepcopy(proj).float()
+    twin_opt = torch.optim.AdamW(twin_proj.parameters(), lr=1e-3, weight_decay=0.0)
+    feats = torch.randn(2, 24, 32, device=cuda_dev, dtype=torch.bfloat16)
+    model.train()
+    for step in range(3):
+        sync.begin_step()
+        emb = proj(feats)                                                       # [2, 24, 256] image-token embeddings
+        out = model(inputs_embeds=emb, labels=torch.randint(0, 512, (2, 24), device=cuda_dev))
+        out.loss.backward()
+        # reference: ONE global norm over LoRA grads + projector grads
+        lora_sq = sum(float(p.grad.float().pow(2).sum()) for (_, p, _) in sync.slots)
+        extra_sq = sum(float(p.grad.float().pow(2).sum()) for p in proj.parameters())
+        want = (lora_sq + extra_sq) ** 0.5
+        assert extra_sq > 0
+        max_norm = 0.5 * want                                                   # make the clip bite
+        g_before = [p.grad.detach().float().clone() for p in proj.parameters()]
+        got = float(opt.clip_grad_norm_(max_norm))
+        assert abs(got - want) <= 5e-3 * want, (got, want)
+        opt.step()
+        coef = max_norm / (want + 1e-6)
+        for tp, g in zip(twin_proj.parameters(), g_before):
+            tp.grad = g * coef
+        twin_opt.step()
+        for p, tp in zip(proj.parameters(), twin_proj.parameters()):
+            err = float((p.detach().float() - tp.detach()).abs().max())
+            assert err <= 2 ** -7 * float(tp.detach().abs().max()) + 1e-6, (step, err)
+            with torch.no_grad():
+                tp.copy_(p.detach().float())
+        opt.zero_grad()
+        assert all(p.grad is None for p in proj.parameters())
