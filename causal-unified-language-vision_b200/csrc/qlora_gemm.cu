@@ -505,46 +505,6 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
         return 0;
     };
     auto slab = [&](int tile_m) { int g = static_cast<int>((32ll << 20) / (2ll * N * tile_m)); return g < 1 ? 1 : g; };
-    // Experiment (B2Q_DX_L2_PERSIST=<MB>, default off): keep part of dx resident in the L2 between the decode GEMM that
-    // writes it and the masked GEMM that read-modify-writes it (access-policy window on the caller's stream for the two
-    // launches, persisting set-aside of the given size), so that fewer reductions pull their line back from HBM.
-    static const int persist_mb = env_int("B2Q_DX_L2_PERSIST", 0);
-    bool window_set = false;
-    if (masked && persist_mb > 0) {
-        static std::atomic<uint64_t> limit_set{0};
-        const int dev = current_device();
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        size_t want = static_cast<size_t>(persist_mb) << 20;
-        if (want > static_cast<size_t>(max_persist)) want = static_cast<size_t>(max_persist);
-        if (want > 0 && max_window > 0) {
-            const uint64_t bit = 1ull << (dev & 63);
-            if ((limit_set.load(std::memory_order_relaxed) & bit) == 0) {
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-                limit_set.fetch_or(bit, std::memory_order_relaxed);
-            }
-            size_t bytes = static_cast<size_t>(M) * K * 2;
-            if (bytes > static_cast<size_t>(max_window)) bytes = static_cast<size_t>(max_window);
-            cudaStreamAttrValue v{};
-            v.accessPolicyWindow.base_ptr = dx;
-            v.accessPolicyWindow.num_bytes = bytes;
-            v.accessPolicyWindow.hitRatio = static_cast<float>(want) / static_cast<float>(bytes) > 1.f ? 1.f : static_cast<float>(want) / static_cast<float>(bytes);
-            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            window_set = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
-            if (!window_set) (void)cudaGetLastError();
-        }
-    }
-    struct WindowGuard {   // the caller's stream gets its (empty) access-policy window back on every way out
-        cudaStream_t stream; bool* set;
-        ~WindowGuard() {
-            if (!*set) return;
-            cudaStreamAttrValue v{};
-            v.accessPolicyWindow.num_bytes = 0;
-            cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
-        }
-    } window_guard{stream, &window_set};
     switch (variant) {
         case 0: if ((e = setup(DxV0::BNC, slab(DxV0::TILE_M)))) return e; e = launch<DxV0>(p, stream); break;
         case 1: if ((e = setup(DxV1::BNC, slab(DxV1::TILE_M)))) return e; e = launch<DxV1>(p, stream); break;
