@@ -65,6 +65,8 @@ struct GemmParams {
     int tile_m;        // row stride between m-tiles, <= TILE_M (load-balancing of the skinny kernels: a tile still
                        // loads and multiplies TILE_M rows, but only stores its first tile_m -- the rest belong to the next tile)
     int accum_d;       // EPI_BF16: D = bf16(D + alpha * acc)  (read-modify-write of the caller's buffer)
+    int stream_out;    // staged epilogue: store D with the streaming (evict-first) hint -- the output is not read again by the
+                       // next kernel of the path, so it should not push the operands that ARE re-read out of the L2
     // LoRA dropout (A_XF transform / EPI_BF16_MASK): keep(i) for element i = row * xf_ld + col of the
     // activation the mask belongs to (b2q_internal.h dropout_keep)
     unsigned long long seed;
@@ -522,6 +524,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) qlora_gemm_kernel(const __gri
                             for (int i = 0; i < 8; ++i) {
                                 const uint32_t ok = (row_w + i * 4 < M_r && (val[i].x | val[i].y | val[i].z | val[i].w) != 0u) ? 1u : 0u;
                                 asm volatile("{\n\t.reg .pred P1;\n\tsetp.ne.b32 P1, %5, 0;\n\t@P1 red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};\n\t}\n"
+                                             ::"l"(gp + static_cast<long long>(i) * 4 * ldd_r), "r"(val[i].x), "r"(val[i].y),
+                                               "r"(val[i].z), "r"(val[i].w), "r"(ok) : "memory");
+                            }
+                        } else if (p.stream_out) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t ok = (row_w + i * 4 < M_r) ? 1u : 0u;
+                                asm volatile("{\n\t.reg .pred P1;\n\tsetp.ne.b32 P1, %5, 0;\n\t@P1 st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};\n\t}\n"
                                              ::"l"(gp + static_cast<long long>(i) * 4 * ldd_r), "r"(val[i].x), "r"(val[i].y),
                                                "r"(val[i].z), "r"(val[i].w), "r"(ok) : "memory");
                             }
