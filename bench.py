@@ -172,13 +172,6 @@ def main():
         run_reference(args, world, rank)
         return
 
-    if world > 1 and os.environ.get("B2Q_BENCH_ISOLATE_GPU") == "1":
-        # diagnostic (tools/gpu_multi_diag.sh): every rank sees only its own GPU, as in the single-GPU runs -- one autograd
-        # device thread, no CUDA context on a foreign GPU.  Must happen before CUDA is initialised.
-        visible = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v != ""]
-        os.environ["CUDA_VISIBLE_DEVICES"] = visible[local_rank] if len(visible) > local_rank else str(local_rank)
-        local_rank = 0
-
     import torch
     import torch.distributed as dist
     from importlib import import_module
