@@ -1,7 +1,6 @@
 """Discrete-event model of the main kernels' barrier protocol (qlora_gemm.cuh): operand ring, UMMA issuer, asynchronous
-tensor pipe with tcgen05.commit semantics, epilogue -- for the default issue order (RA = 0) and the reordered one of
-variant 6 (RA = 3).  The roles are hand-ported from the kernel with the SAME index / phase arithmetic (stage `s`, phase
-bit `ph`, the `(s2 < s) ? ph ^ 1 : ph` look-ahead, accumulator phase `aph`); a random scheduler interleaves them and the
+tensor pipe with tcgen05.commit semantics, epilogue.  The roles are hand-ported from the kernel with the SAME index / phase arithmetic (stage `s`, phase
+bit `ph`, accumulator phase `aph`); a random scheduler interleaves them and the
 model checks, over many seeds and shapes:
 
   * no deadlock (every role runs to completion),
@@ -12,8 +11,10 @@ model checks, over many seeds and shapes:
 
 Also modelled, with the same checks: the double-buffered, two-epilogue-set variant (masked dX GEMM), the transform-group
 ring of the LoRA-dropout kernels (4 groups over a 6-stage ring), and the decode kernels' operand + packed rings with two
-decode groups and LoRA tail k-blocks (the `it` / `pit` position arithmetic).  Each model is mutation-checked: breaking
-the phase look-ahead, the packed-ring position, the tail ownership or the sub-tile-1 wait makes it fail.
+decode groups and LoRA tail k-blocks (the `it` / `pit` position arithmetic).  Since round 2 TMA loads and
+shared-memory reads complete asynchronously and out of order in the model, and run_all() ends with mutation checks: the
+three protocols that stalled or corrupted on hardware in rounds 1 / 2 (transform groups without the "previous use
+released" wait, packed ring without it at tile boundaries, packed slot released before its read returned) must fail.
 
 Pure Python, no GPU: a design check, run by tests/test_host.py.  It does not model TMA, decode or TMEM timing.
 """
@@ -42,11 +43,11 @@ class Deadlock(Exception):
     pass
 
 
-def simulate(num_tiles, kb_total, ra_cfg, seed):
+def simulate(num_tiles, kb_total, seed):
     rng = random.Random(seed)
     full = [Bar(2) for _ in range(STAGES)]      # producer + decode group
     empty = [Bar(1) for _ in range(STAGES)]     # tcgen05.commit
-    tfull, tfull1 = Bar(1), Bar(1)
+    tfull = Bar(1)
     tempty = [Bar(1) for _ in range(MT)]        # the epilogue as one agent
     stage_content = [None] * STAGES             # (tile, kb) the producer / decode wrote
     stage_ready = [0] * STAGES                  # writers done for the current content (2 = both)
@@ -87,82 +88,20 @@ def simulate(num_tiles, kb_total, ra_cfg, seed):
             pipe.append(("mma", tile, kb, mt, stage))
 
         for tile in range(num_tiles):
-            if ra_cfg == 0:
-                for kb in range(kb_total):
-                    yield from wait(full[s], ph, use[s])
-                    for mt in range(MT):
-                        if kb == 0:
-                            yield from wait(tempty[mt], aph ^ 1, tile - 1) if tile > 0 else iter(())
-                        issue(s, mt, tile, kb)
-                        yield "step"
-                    pipe.append(("commit", empty[s]))
-                    if kb == kb_total - 1:
-                        pipe.append(("commit", tfull))
-                    use[s] += 1
-                    s += 1
-                    if s == STAGES:
-                        s, ph = 0, ph ^ 1
-            else:
-                ra = min(kb_total, ra_cfg)
-                rt = min(kb_total - ra, ra_cfg)
-                # head
-                if tile > 0:
-                    yield from wait(tempty[0], aph ^ 1, tile - 1)
-                s2 = s
-                look = {}
-                for kb in range(ra):
-                    yield from wait(full[s2], (ph ^ 1) if s2 < s else ph, use[s2])
-                    look[kb] = s2
-                    issue(s2, 0, tile, kb)
-                    if kb == kb_total - 1:
-                        pipe.append(("commit", tfull))
+            for kb in range(kb_total):
+                yield from wait(full[s], ph, use[s])
+                for mt in range(MT):
+                    if kb == 0:
+                        yield from wait(tempty[mt], aph ^ 1, tile - 1) if tile > 0 else iter(())
+                    issue(s, mt, tile, kb)
                     yield "step"
-                    s2 = (s2 + 1) % STAGES
-                if tile > 0:
-                    yield from wait(tempty[1], aph ^ 1, tile - 1)
-                for kb in range(ra):
-                    assert look[kb] == s
-                    issue(s, 1, tile, kb)
-                    pipe.append(("commit", empty[s]))
-                    if kb == kb_total - 1:
-                        pipe.append(("commit", tfull1))
-                    use[s] += 1
-                    yield "step"
-                    s += 1
-                    if s == STAGES:
-                        s, ph = 0, ph ^ 1
-                kb_end = kb_total - rt
-                for kb in range(ra, kb_end):
-                    yield from wait(full[s], ph, use[s])
-                    for mt in range(MT):
-                        issue(s, mt, tile, kb)
-                        if mt == 0 and kb == kb_total - 1:
-                            pipe.append(("commit", tfull))
-                        yield "step"
-                    pipe.append(("commit", empty[s]))
-                    if kb == kb_total - 1:
-                        pipe.append(("commit", tfull1))
-                    use[s] += 1
-                    s += 1
-                    if s == STAGES:
-                        s, ph = 0, ph ^ 1
-                if rt > 0:
-                    s2 = s
-                    for kb in range(kb_end, kb_total):
-                        yield from wait(full[s2], (ph ^ 1) if s2 < s else ph, use[s2])
-                        issue(s2, 0, tile, kb)
-                        yield "step"
-                        s2 = (s2 + 1) % STAGES
+                pipe.append(("commit", empty[s]))
+                if kb == kb_total - 1:
                     pipe.append(("commit", tfull))
-                    for kb in range(kb_end, kb_total):
-                        issue(s, 1, tile, kb)
-                        pipe.append(("commit", empty[s]))
-                        use[s] += 1
-                        yield "step"
-                        s += 1
-                        if s == STAGES:
-                            s, ph = 0, ph ^ 1
-                    pipe.append(("commit", tfull1))
+                use[s] += 1
+                s += 1
+                if s == STAGES:
+                    s, ph = 0, ph ^ 1
             aph ^= 1
         log["issuer_done"] = True
 
@@ -171,8 +110,6 @@ def simulate(num_tiles, kb_total, ra_cfg, seed):
         for tile in range(num_tiles):
             yield from wait(tfull, aph, tile)
             for mt in range(MT):
-                if ra_cfg > 0 and mt == 1:
-                    yield from wait(tfull1, aph, tile)
                 assert acc_mmas.get((tile, mt), 0) == kb_total, f"drain of tile {tile} sub-tile {mt} before its MMAs finished"
                 yield "step"                      # the drain itself takes time
                 acc_drained[(tile, mt)] = True
@@ -211,7 +148,7 @@ def simulate(num_tiles, kb_total, ra_cfg, seed):
             continue
         blocked_rounds = blocked_rounds + 1 if r == "blocked" else 0
         if blocked_rounds > 20000:
-            raise Deadlock(f"roles still alive: {sorted(agents)} (tiles {num_tiles}, kb {kb_total}, RA {ra_cfg}, seed {seed})")
+            raise Deadlock(f"roles still alive: {sorted(agents)} (tiles {num_tiles}, kb {kb_total}, seed {seed})")
     assert all(acc_drained.get((t, m)) for t in range(num_tiles) for m in range(MT))
     return log["waits"]
 
@@ -579,12 +516,11 @@ def simulate_decode(num_tiles, kb_main, kb_tail, seed, stages=4, pst=4, ng=2, gu
 
 def run_all(seeds=12):
     n = 0
-    for ra in (0, 3):
-        for kb_total in (1, 2, 3, 4, 5, 6, 7, 9, 17):
-            for tiles in (1, 2, 3, 5):
-                for seed in range(seeds):
-                    simulate(tiles, kb_total, ra, seed)
-                    n += 1
+    for kb_total in (1, 2, 3, 4, 5, 6, 7, 9, 17):
+        for tiles in (1, 2, 3, 5):
+            for seed in range(seeds):
+                simulate(tiles, kb_total, seed)
+                n += 1
     for kb_total in (1, 2, 3):
         for tiles in (1, 2, 3, 4, 7):
             for seed in range(seeds):

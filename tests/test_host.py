@@ -192,16 +192,17 @@ def test_bench_control_flow_dry_run(extra):
 
 
 def test_pipeline_protocol_model():
-    """tests/sim_pipeline_protocol.py: the operand-ring / accumulator barrier protocol of the main kernels, default and
-    variant-6 issue order, runs to completion under random interleavings with no phase aliasing and no operand or
-    accumulator hazard."""
+    """tests/sim_pipeline_protocol.py: the barrier protocols of the kernel family (operand ring + accumulator, two epilogue
+    sets, transform groups, decode groups + packed ring) run to completion under random interleavings AND out-of-order
+    load completion with no phase aliasing and no operand / accumulator hazard -- and the three round-1 protocols that
+    stalled or corrupted on hardware fail in the model (its own mutation checks)."""
     import importlib.util
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sim_pipeline_protocol.py")
     spec = importlib.util.spec_from_file_location("sim_pipeline_protocol", path)
     sim = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(sim)
-    assert sim.run_all(seeds=6) == 2 * 9 * 4 * 6
+    assert sim.run_all(seeds=6) == 9 * 4 * 6
 
 
 def test_reference_arm_prints_the_contract_line():
