@@ -265,6 +265,12 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// Activation bytes per L2 slab of the two main kernels' rasterisation (B2Q_SLAB_MB, default 32)
+static long long slab_bytes() {
+    static const long long b = static_cast<long long>(env_int("B2Q_SLAB_MB", 32)) << 20;
+    return b > 0 ? b : (32ll << 20);
+}
+
 static void fill_weight(GemmParams& p, const b2q_nf4_weight* w, int K_w) {
     p.am.absmax_f32 = w->absmax;
     p.am.absmax_q = w->absmax_q;
@@ -463,7 +469,7 @@ extern "C" int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void*
         return 0;
     };
     // L2 slab: keep (group_m * TILE_M) x K of activations (bf16) around 32 MB
-    auto slab = [&](int tile_m) { int g = static_cast<int>((32ll << 20) / (2ll * K * tile_m)); return g < 1 ? 1 : g; };
+    auto slab = [&](int tile_m) { int g = static_cast<int>((slab_bytes()) / (2ll * K * tile_m)); return g < 1 ? 1 : g; };
     switch (variant) {
         case 0: if ((e = setup(FwdV0::BNC, slab(FwdV0::TILE_M)))) return e; return launch<FwdV0>(p, stream);
         case 1: if ((e = setup(FwdV1::BNC, slab(FwdV1::TILE_M)))) return e; return launch<FwdV1>(p, stream);
@@ -510,7 +516,7 @@ extern "C" int b2q_qlora_bwd_dx(const void* dy, const b2q_nf4_weight* w, const v
         }
         return 0;
     };
-    auto slab = [&](int tile_m) { int g = static_cast<int>((32ll << 20) / (2ll * N * tile_m)); return g < 1 ? 1 : g; };
+    auto slab = [&](int tile_m) { int g = static_cast<int>((slab_bytes()) / (2ll * N * tile_m)); return g < 1 ? 1 : g; };
     switch (variant) {
         case 0: if ((e = setup(DxV0::BNC, slab(DxV0::TILE_M)))) return e; e = launch<DxV0>(p, stream); break;
         case 1: if ((e = setup(DxV1::BNC, slab(DxV1::TILE_M)))) return e; e = launch<DxV1>(p, stream); break;
