@@ -265,10 +265,15 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-// Activation bytes per L2 slab of the two main kernels' rasterisation (B2Q_SLAB_MB, default 32)
+// Activation bytes per L2 slab of the two main kernels' rasterisation (B2Q_SLAB_MB).  The slab of m-tiles is what all n-tiles
+// of it re-read from the L2.  Round 2, ncu at M = 16384, 4096 x 4096: DRAM reads per launch 150 / 160 / 253 / 484 MB for
+// slabs of 8 / 16 / 32 / 64 MB against 143 MB of operands -- with 32 MB (round 1's choice) the activation was fetched from
+// HBM twice, with 64 MB three and a half times: what this access pattern gets out of the 126 MB L2 is about half of it
+// (two partitions, shared read data ends up in both).  Step time: 16 MB 0.5 % faster than 32 MB, 64 MB 2.6 % slower, 8-24 MB
+// within noise of each other.
 static long long slab_bytes() {
-    static const long long b = static_cast<long long>(env_int("B2Q_SLAB_MB", 32)) << 20;
-    return b > 0 ? b : (32ll << 20);
+    static const long long b = static_cast<long long>(env_int("B2Q_SLAB_MB", 16)) << 20;
+    return b > 0 ? b : (16ll << 20);
 }
 
 static void fill_weight(GemmParams& p, const b2q_nf4_weight* w, int K_w) {
@@ -468,7 +473,7 @@ extern "C" int b2q_qlora_fwd(const void* x, const b2q_nf4_weight* w, const void*
         }
         return 0;
     };
-    // L2 slab: keep (group_m * TILE_M) x K of activations (bf16) around 32 MB
+    // L2 slab: keep (group_m * TILE_M) x K of activations (bf16) around slab_bytes()
     auto slab = [&](int tile_m) { int g = static_cast<int>((slab_bytes()) / (2ll * K * tile_m)); return g < 1 ? 1 : g; };
     switch (variant) {
         case 0: if ((e = setup(FwdV0::BNC, slab(FwdV0::TILE_M)))) return e; return launch<FwdV0>(p, stream);
